@@ -1,0 +1,391 @@
+"""CPU oracle for the LC-Rec item-indexing hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a numpy restatement of the reference algorithm.  It is the checker
+the CUDA path is compared with; nothing under ``lcrec_b200/`` may import it.
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it.
+
+Parity status: PINNED.  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so the oracle is pinned against outputs of the unmodified
+reference code itself, imported from /root/reference in the build container by
+``oracle/make_golden.py`` and committed under ``tests/golden/``
+(``tests/test_oracle_golden.py`` is the check).
+
+Every function cites the reference lines it restates (paths relative to
+/root/reference).  fp32 everywhere the reference is fp32, fp64 for Sinkhorn,
+int64 indices, lowest index on ties.
+"""
+from __future__ import annotations
+
+import json
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+F32 = np.float32
+F64 = np.float64
+
+TOKEN_PREFIX = ("<a_{}>", "<b_{}>", "<c_{}>", "<d_{}>", "<e_{}>")  # index/generate_indices.py:83
+
+
+# --------------------------------------------------------------------------- #
+# parameters
+# --------------------------------------------------------------------------- #
+@dataclass
+class MlpParams:
+    """Weights of one ``MLPLayers`` stack (index/models/layers.py:7-43).
+
+    ``weights[i]`` is (out_i, in_i) like ``nn.Linear.weight``; ``bn`` holds, per
+    non-final layer, (gamma, beta, running_mean, running_var, eps) or None.
+    """
+    weights: List[np.ndarray]
+    biases: List[np.ndarray]
+    bn: Optional[List[Optional[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray, float]]]] = None
+
+
+@dataclass
+class RqvaeParams:
+    encoder: MlpParams
+    codebooks: List[np.ndarray]            # L arrays (K_l, D) fp32, rq.vq_layers.{l}.embedding.weight
+    sk_epsilons: List[float]
+    sk_iters: int = 50
+    beta: float = 0.25
+    decoder: Optional[MlpParams] = None
+    quant_loss_weight: float = 1.0
+    loss_type: str = "mse"
+
+
+def params_from_state_dict(sd: Dict[str, np.ndarray], sk_epsilons: Sequence[float], sk_iters: int,
+                           beta: float = 0.25, bn_eps: float = 1e-5,
+                           quant_loss_weight: float = 1.0, loss_type: str = "mse") -> RqvaeParams:
+    """Build oracle parameters from a reference ``RQVAE.state_dict()`` (numpy values).
+
+    Key layout: ``encoder.mlp_layers.{i}.weight|bias`` for Linear,
+    ``...{i}.running_mean`` etc. for BatchNorm1d, ``rq.vq_layers.{l}.embedding.weight``.
+    """
+    def mlp(prefix: str) -> Optional[MlpParams]:
+        idxs = sorted({int(k.split(".")[2]) for k in sd if k.startswith(prefix + ".mlp_layers.")})
+        if not idxs:
+            return None
+        lin, bns = [], {}
+        for i in idxs:
+            base = f"{prefix}.mlp_layers.{i}"
+            if base + ".running_mean" in sd:
+                bns[len(lin) - 1] = (sd[base + ".weight"].astype(F32), sd[base + ".bias"].astype(F32),
+                                     sd[base + ".running_mean"].astype(F32),
+                                     sd[base + ".running_var"].astype(F32), bn_eps)
+            else:
+                lin.append((sd[base + ".weight"].astype(F32), sd[base + ".bias"].astype(F32)))
+        bn = [bns.get(j) for j in range(len(lin))] if bns else None
+        return MlpParams([w for w, _ in lin], [b for _, b in lin], bn)
+
+    n_levels = len({k.split(".")[2] for k in sd if k.startswith("rq.vq_layers.")})
+    cbs = [sd[f"rq.vq_layers.{l}.embedding.weight"].astype(F32) for l in range(n_levels)]
+    return RqvaeParams(encoder=mlp("encoder"), codebooks=cbs, sk_epsilons=list(sk_epsilons),
+                       sk_iters=sk_iters, beta=beta, decoder=mlp("decoder"),
+                       quant_loss_weight=quant_loss_weight, loss_type=loss_type)
+
+
+# --------------------------------------------------------------------------- #
+# a2: MLP
+# --------------------------------------------------------------------------- #
+def mlp_forward(x: np.ndarray, p: MlpParams, training_bn: bool = False) -> np.ndarray:
+    """Eval-mode ``MLPLayers.forward`` (index/models/layers.py:18-43), relu activation.
+
+    Per layer: Dropout (identity in eval / p=0) -> Linear -> [BatchNorm1d unless last]
+    -> [ReLU unless last] (layers.py:22-30).  fp32 throughout like ``nn.Linear``.
+    """
+    h = np.ascontiguousarray(x, dtype=F32)
+    last = len(p.weights) - 1
+    for i, (w, b) in enumerate(zip(p.weights, p.biases)):
+        h = h @ w.T.astype(F32) + b.astype(F32)
+        if i != last:
+            if p.bn is not None and p.bn[i] is not None:
+                g, bt, mu, var, eps = p.bn[i]
+                if training_bn:  # batch statistics, biased variance (torch BatchNorm1d training)
+                    mu = h.mean(axis=0, dtype=F64).astype(F32)
+                    var = h.var(axis=0, dtype=F64).astype(F32)
+                h = (h - mu) / np.sqrt(var + F32(eps)).astype(F32) * g + bt
+                h = h.astype(F32)
+            h = np.maximum(h, F32(0))
+    return h.astype(F32)
+
+
+# --------------------------------------------------------------------------- #
+# a4/a5/a6/a7: one quantiser level
+# --------------------------------------------------------------------------- #
+def vq_distances(latent: np.ndarray, codebook: np.ndarray) -> np.ndarray:
+    """``d = sum(x^2) + sum(c^2)^T - 2 x c^T`` in fp32, evaluation order (xx + cc) - 2 dot
+    (index/models/vq.py:71-73)."""
+    latent = latent.astype(F32, copy=False)
+    codebook = codebook.astype(F32, copy=False)
+    xx = np.sum(latent * latent, axis=1, keepdims=True, dtype=F32)
+    cc = np.sum(codebook * codebook, axis=1, keepdims=True, dtype=F32).T
+    dot = latent @ codebook.T
+    return ((xx + cc) - F32(2) * dot).astype(F32)
+
+
+def center_distance_for_constraint(d: np.ndarray) -> np.ndarray:
+    """Global max/min centring over the whole (B, K) matrix, fp32 (index/models/vq.py:51-61)."""
+    d = d.astype(F32, copy=False)
+    mx = d.max()
+    mn = d.min()
+    middle = F32((mx + mn) / F32(2))
+    amplitude = F32(F32(mx - middle) + F32(1e-5))
+    if not amplitude > 0:
+        raise AssertionError("amplitude > 0")  # vq.py:59
+    return ((d - middle) / amplitude).astype(F32)
+
+
+def sinkhorn_algorithm(distances: np.ndarray, epsilon: float, sinkhorn_iterations: int) -> np.ndarray:
+    """Literal restatement of ``sinkhorn_algorithm`` (index/models/layers.py:85-108).
+
+    The code (not its swapped comments) is authoritative: per iteration divide by the
+    per-row sum (dim=1), by B, by the per-column sum (dim=0), by K; finally multiply by B.
+    Works in the dtype of ``distances`` (fp64 at the call site vq.py:78-79).
+    """
+    dist = np.asarray(distances)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore", under="ignore"):
+        q = np.exp(-dist / epsilon)
+        n_rows, n_cols = q.shape
+        q = q / q.sum(axis=-1, keepdims=True).sum(axis=-2, keepdims=True)
+        for _ in range(sinkhorn_iterations):
+            q = q / q.sum(axis=1, keepdims=True)
+            q = q / n_rows
+            q = q / q.sum(axis=0, keepdims=True)
+            q = q / n_cols
+        q = q * n_rows
+    return q
+
+
+def _argmax_first_nan_wins(q: np.ndarray) -> np.ndarray:
+    """``torch.argmax`` semantics: first maximal index; a NaN counts as the maximum."""
+    nan = np.isnan(q)
+    idx = np.argmax(np.where(nan, np.inf, q), axis=-1)
+    has_nan = nan.any(axis=-1)
+    if has_nan.any():
+        idx = np.where(has_nan, np.argmax(nan, axis=-1), idx)
+    return idx.astype(np.int64)
+
+
+def vq_assign(latent: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: float,
+              sk_iters: int, want_q: bool = False):
+    """Index selection of ``VectorQuantizer.forward`` (index/models/vq.py:71-83)."""
+    d = vq_distances(latent, codebook)
+    if (not use_sk) or sk_epsilon <= 0:
+        idx = np.argmin(d, axis=-1).astype(np.int64)   # first minimum, like torch.argmin
+        return (idx, d, None) if want_q else idx
+    dc = center_distance_for_constraint(d).astype(F64)
+    q = sinkhorn_algorithm(dc, sk_epsilon, sk_iters)
+    idx = _argmax_first_nan_wins(q)
+    return (idx, d, q) if want_q else idx
+
+
+def _mse(a: np.ndarray, b: np.ndarray) -> np.float32:
+    """``F.mse_loss(..., reduction='mean')`` in fp32 (accumulated in fp64 here, rounded once)."""
+    diff = a.astype(F32) - b.astype(F32)
+    return F32(np.mean((diff * diff).astype(F32), dtype=F64))
+
+
+def vq_forward(x: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: float, sk_iters: int,
+               beta: float):
+    """Forward values of ``VectorQuantizer.forward`` (index/models/vq.py:63-99).
+
+    Returns (x_q straight-through forward value ``x + (q - x)``, loss, indices).
+    """
+    x = x.astype(F32, copy=False)
+    idx = vq_assign(x, codebook, use_sk, sk_epsilon, sk_iters)
+    q = codebook.astype(F32)[idx]
+    mse = _mse(q, x)
+    loss = F32(mse + F32(beta) * mse)          # codebook_loss + beta * commitment_loss (vq.py:90-92)
+    x_q = (x + (q - x)).astype(F32)            # vq.py:95
+    return x_q, loss, idx
+
+
+# --------------------------------------------------------------------------- #
+# a9/a10: residual quantiser and the model
+# --------------------------------------------------------------------------- #
+def rq_forward(z: np.ndarray, p: RqvaeParams, use_sk: bool):
+    """``ResidualVectorQuantizer.forward`` (index/models/rq.py:39-56)."""
+    residual = z.astype(F32, copy=True)
+    x_q = np.zeros_like(residual)
+    losses, indices = [], []
+    for cb, eps in zip(p.codebooks, p.sk_epsilons):
+        x_res, loss, idx = vq_forward(residual, cb, use_sk, eps, p.sk_iters, p.beta)
+        residual = (residual - x_res).astype(F32)
+        x_q = (x_q + x_res).astype(F32)
+        losses.append(loss)
+        indices.append(idx)
+    mean_loss = F32(np.mean(np.array(losses, dtype=F32), dtype=F64))
+    return x_q, mean_loss, np.stack(indices, axis=-1)
+
+
+def rq_trace(z: np.ndarray, p: RqvaeParams):
+    """argmin-only pass that also returns the residual entering every level (teacher forcing)."""
+    residual = z.astype(F32, copy=True)
+    resids, dists, idxs = [], [], []
+    for cb in p.codebooks:
+        resids.append(residual.copy())
+        d = vq_distances(residual, cb)
+        idx = np.argmin(d, axis=-1).astype(np.int64)
+        q = cb.astype(F32)[idx]
+        x_res = (residual + (q - residual)).astype(F32)
+        residual = (residual - x_res).astype(F32)
+        dists.append(d)
+        idxs.append(idx)
+    return resids, dists, np.stack(idxs, axis=-1)
+
+
+def get_indices(x: np.ndarray, p: RqvaeParams, use_sk: bool = False) -> np.ndarray:
+    """``RQVAE.get_indices`` (index/models/rqvae.py:68-72)."""
+    z = mlp_forward(x, p.encoder)
+    return rq_forward(z, p, use_sk)[2]
+
+
+def rqvae_forward(x: np.ndarray, p: RqvaeParams, use_sk: bool = True):
+    """``RQVAE.forward`` + ``compute_loss`` forward values (index/models/rqvae.py:61-85)."""
+    z = mlp_forward(x, p.encoder)
+    x_q, rq_loss, idx = rq_forward(z, p, use_sk)
+    out = mlp_forward(x_q, p.decoder)
+    if p.loss_type == "mse":
+        recon = _mse(out, x)
+    elif p.loss_type == "l1":
+        recon = F32(np.mean(np.abs(out.astype(F32) - x.astype(F32)), dtype=F64))
+    else:
+        raise ValueError("incompatible loss type")   # rqvae.py:81
+    total = F32(recon + F32(p.quant_loss_weight) * rq_loss)
+    return out, rq_loss, idx, total, recon
+
+
+# --------------------------------------------------------------------------- #
+# a12/a14: collision bookkeeping
+# --------------------------------------------------------------------------- #
+def collision_groups(codes: np.ndarray) -> List[List[int]]:
+    """``get_collision_item`` (index/generate_indices.py:29-42): lists of item ids sharing an
+    identical code tuple, groups in first-occurrence order, members ascending."""
+    table: Dict[bytes, List[int]] = {}
+    c = np.ascontiguousarray(codes, dtype=np.int64)
+    for i in range(c.shape[0]):
+        table.setdefault(c[i].tobytes(), []).append(i)
+    return [g for g in table.values() if len(g) > 1]
+
+
+def n_unique_codes(codes: np.ndarray) -> int:
+    return int(np.unique(np.ascontiguousarray(codes, dtype=np.int64), axis=0).shape[0])
+
+
+def collision_rate(codes: np.ndarray) -> float:
+    """(N - |unique|) / N (index/trainer.py:150, index/generate_indices.py:133-136)."""
+    n = codes.shape[0]
+    return (n - n_unique_codes(codes)) / n
+
+
+def max_conflicts(codes: np.ndarray) -> int:
+    """``max(get_indices_count(...).values())`` (index/generate_indices.py:23-27,132)."""
+    _, cnt = np.unique(np.ascontiguousarray(codes, dtype=np.int64), axis=0, return_counts=True)
+    return int(cnt.max())
+
+
+# --------------------------------------------------------------------------- #
+# a15/a16: generate_indices
+# --------------------------------------------------------------------------- #
+@dataclass
+class GenTrace:
+    codes_pass0: np.ndarray
+    rounds: List[np.ndarray] = field(default_factory=list)   # code table after each round
+    n_groups: List[int] = field(default_factory=list)
+    n_rows: List[int] = field(default_factory=list)
+
+
+def generation_epsilons(p: RqvaeParams) -> List[float]:
+    """index/generate_indices.py:101-105: levels 0..L-2 -> 0; last keeps its value, 0 -> 0.003."""
+    eps = [0.0] * (len(p.codebooks) - 1)
+    last = p.sk_epsilons[-1]
+    eps.append(0.003 if last == 0.0 else last)
+    return eps
+
+
+def generate_indices(x: np.ndarray, p: RqvaeParams, batch_size: int = 64, max_rounds: int = 20,
+                     reencode: bool = True) -> Tuple[np.ndarray, GenTrace]:
+    """``index/generate_indices.py:85-128``.
+
+    PASS 0: argmin codes for all items in batches of ``batch_size`` (:85-95).
+    Then up to ``max_rounds`` rounds: every collision group is re-quantised on its own with
+    Sinkhorn on the last level, all L codes of its members overwritten (:107-128).
+
+    ``reencode=True`` follows the reference literally (encoder re-run on the group's rows);
+    ``reencode=False`` re-uses the latents of PASS 0 (what the CUDA path does: same maths, the
+    difference is GEMM batch-shape rounding only).
+    """
+    x = np.ascontiguousarray(x, dtype=F32)
+    n = x.shape[0]
+    codes = np.empty((n, len(p.codebooks)), dtype=np.int64)
+    latents = np.empty((n, p.codebooks[0].shape[1]), dtype=F32) if not reencode else None
+    for s in range(0, n, batch_size):
+        z = mlp_forward(x[s:s + batch_size], p.encoder)
+        if latents is not None:
+            latents[s:s + batch_size] = z
+        codes[s:s + batch_size] = rq_forward(z, p, use_sk=False)[2]
+    trace = GenTrace(codes_pass0=codes.copy())
+
+    p_sk = RqvaeParams(encoder=p.encoder, codebooks=p.codebooks, sk_epsilons=generation_epsilons(p),
+                       sk_iters=p.sk_iters, beta=p.beta)
+    tt = 0
+    while tt < max_rounds and n_unique_codes(codes) != n:
+        groups = collision_groups(codes)
+        rows = 0
+        for g in groups:
+            z = mlp_forward(x[g], p.encoder) if reencode else latents[g]
+            codes[g] = rq_forward(z, p_sk, use_sk=True)[2]
+            rows += len(g)
+        trace.rounds.append(codes.copy())
+        trace.n_groups.append(len(groups))
+        trace.n_rows.append(rows)
+        tt += 1
+    return codes, trace
+
+
+def codes_to_tokens(codes: np.ndarray) -> List[List[str]]:
+    """``prefix[i].format(int(ind))`` (index/generate_indices.py:83,90-92)."""
+    return [[TOKEN_PREFIX[i].format(int(v)) for i, v in enumerate(row)] for row in codes]
+
+
+def index_json(codes: np.ndarray) -> str:
+    """Exactly what ``json.dump({item: [tokens]})`` writes (index/generate_indices.py:138-145)."""
+    return json.dumps({i: toks for i, toks in enumerate(codes_to_tokens(codes))})
+
+
+# --------------------------------------------------------------------------- #
+# near-tie accounting used by the parity tests
+# --------------------------------------------------------------------------- #
+def top2_relative_gap(d: np.ndarray) -> np.ndarray:
+    """Relative gap between the two smallest distances of each row (north_star near-tie rule)."""
+    part = np.partition(d.astype(F64), 1, axis=-1)[:, :2]
+    lo, hi = part[:, 0], part[:, 1]
+    denom = np.maximum(np.abs(hi), np.finfo(F64).tiny)
+    return (hi - lo) / denom
+
+
+def classify_code_mismatches(z: np.ndarray, p: RqvaeParams, codes_ours: np.ndarray,
+                             rel_tol: float = 1e-5) -> Tuple[int, int]:
+    """Compare argmin codes with the oracle's on latents ``z``.
+
+    Returns (near_tie_mismatches, hard_mismatches).  A differing row counts as a near-tie when,
+    at the first level where the codes differ, the oracle's top-2 distance gap is below
+    ``rel_tol`` relative (deeper levels of that row are then expected to differ as well).
+    """
+    resids, dists, codes_ref = rq_trace(z, p)
+    near = hard = 0
+    bad = np.nonzero((codes_ref != codes_ours).any(axis=1))[0]
+    for i in bad:
+        lvl = int(np.nonzero(codes_ref[i] != codes_ours[i])[0][0])
+        gap = top2_relative_gap(dists[lvl][i:i + 1])[0]
+        # also accept when our pick is within rel_tol of the oracle's minimum
+        drow = dists[lvl][i].astype(F64)
+        alt = abs(drow[codes_ours[i, lvl]] - drow.min()) / max(abs(drow[codes_ours[i, lvl]]), 1e-300)
+        if gap < rel_tol or alt < rel_tol:
+            near += 1
+        else:
+            hard += 1
+    return near, hard

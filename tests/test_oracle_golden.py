@@ -1,0 +1,99 @@
+"""Pin the numpy oracle against outputs of the unmodified reference (tests/golden, produced by
+oracle/make_golden.py).  CPU only."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import lcrec_oracle as O
+from tests.conftest import state_dict_of
+from lcrec_b200.synth import seeded_weights, synth_items
+
+
+def test_sinkhorn_matches_reference(golden):
+    g = golden("sinkhorn_kat")
+    for ci, (n, k, eps, iters) in enumerate(g["meta"]):
+        d32 = g[f"d_{ci}"]
+        dc = O.center_distance_for_constraint(d32)
+        np.testing.assert_allclose(dc, g[f"dc_{ci}"], rtol=0, atol=2e-7)
+        # teacher-forced: reference centred distances in, exact argmax out
+        q = O.sinkhorn_algorithm(g[f"dc_{ci}"].astype(np.float64), float(eps), int(iters))
+        arg = O._argmax_first_nan_wins(q)
+        assert (arg == g[f"arg_{ci}"]).all(), f"case {ci}"
+        qr = g[f"q_{ci}"]
+        np.testing.assert_allclose(q[: qr.shape[0]], qr, rtol=1e-9, atol=1e-300)
+
+
+def test_sinkhorn_exact_ties_present(golden):
+    """F3: duplicate rows give bit-exact ties that the lowest index must win."""
+    g = golden("sinkhorn_kat")
+    q = g["q_7"]
+    assert (q[0] == q[1]).all() and (q[1] == q[2]).all()
+    assert g["arg_7"][0] == g["arg_7"][1] == g["arg_7"][2]
+
+
+@pytest.mark.parametrize("name", ["small_model", "bn_model"])
+def test_model_forward_matches_reference(golden, name):
+    g = golden(name)
+    p = O.params_from_state_dict(state_dict_of(g), g["sk_epsilons"].tolist(), int(g["sk_iters"]))
+    z = O.mlp_forward(g["x"], p.encoder)
+    np.testing.assert_allclose(z, g["latents"], rtol=2e-5, atol=2e-6)
+    # teacher-forced RQ on reference latents
+    xq, loss, idx = O.rq_forward(g["latents"], p, use_sk=False)
+    near, hard = O.classify_code_mismatches(g["latents"], p, g["codes_argmin_full"])
+    assert hard == 0 and near <= 2
+    assert (idx != g["codes_argmin_full"]).any(axis=1).sum() <= 2
+    np.testing.assert_allclose(xq, g["rq_xq"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(loss, g["rq_loss"], rtol=1e-5)
+    out, rq_loss, fidx, total, recon = O.rqvae_forward(g["x"][:512], p, use_sk=True)
+    assert (fidx != g["fwd_idx"]).any(axis=1).mean() < 0.01
+    np.testing.assert_allclose(recon, g["fwd_recon"], rtol=1e-4)
+    np.testing.assert_allclose(total, g["fwd_total"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["small_model", "bn_model"])
+def test_generate_indices_matches_reference_script(golden, name):
+    g = golden(name)
+    p = O.params_from_state_dict(state_dict_of(g), g["sk_epsilons"].tolist(), int(g["sk_iters"]))
+    codes, trace = O.generate_indices(g["x"], p, batch_size=64, max_rounds=20, reencode=True)
+    assert (trace.codes_pass0 != g["codes_pass0"]).any(axis=1).sum() <= 2
+    # teacher-forced per round: start every round from the reference's table
+    tables = [g["codes_pass0"]] + list(g["rounds"])
+    p_sk = O.RqvaeParams(encoder=p.encoder, codebooks=p.codebooks, sk_epsilons=O.generation_epsilons(p),
+                         sk_iters=p.sk_iters, beta=p.beta)
+    bad_rows = tot_rows = 0
+    for t in range(min(4, len(tables) - 1)):
+        cur = tables[t].copy()
+        for grp in O.collision_groups(cur):
+            cur[grp] = O.rq_forward(O.mlp_forward(g["x"][grp], p.encoder), p_sk, use_sk=True)[2]
+            tot_rows += len(grp)
+        bad_rows += int((cur != tables[t + 1]).any(axis=1).sum())
+    assert bad_rows <= max(2, tot_rows // 500), (bad_rows, tot_rows)
+    # end to end: same collision statistics as the script
+    ref_final = g["script_codes_final"]
+    assert abs(O.collision_rate(codes) - O.collision_rate(ref_final)) < 5e-3
+    assert (codes != ref_final).any(axis=1).mean() < 0.05
+    assert O.index_json(ref_final).encode() == g["script_json"].tobytes()
+
+
+def test_fullshape_matches_reference(golden):
+    g = golden("fullshape")
+    dims = g["dims"].tolist()
+    ws, bs, cbs = seeded_weights(dims, [256] * 4, 32, seed=int(g["seed_w"]))
+    x = synth_items(int(g["n"]), dims[0], n_parents=int(g["n"]) // 8, seed=int(g["seed_x"]))
+    p = O.RqvaeParams(encoder=O.MlpParams(ws, bs), codebooks=cbs, sk_epsilons=[0, 0, 0, 0.003])
+    z = O.mlp_forward(x, p.encoder)
+    np.testing.assert_allclose(z, g["latents"], rtol=1e-4, atol=1e-6)
+    near, hard = O.classify_code_mismatches(g["latents"], p, g["codes"])
+    assert hard == 0
+    codes = O.rq_forward(z, p, use_sk=False)[2]
+    assert (codes != g["codes"]).any(axis=1).sum() <= 2
+
+
+def test_collision_bookkeeping():
+    codes = np.array([[1, 2, 3, 4], [0, 0, 0, 0], [1, 2, 3, 4], [5, 5, 5, 5], [0, 0, 0, 0], [1, 2, 3, 4]])
+    assert O.collision_groups(codes) == [[0, 2, 5], [1, 4]]
+    assert O.n_unique_codes(codes) == 3
+    assert O.max_conflicts(codes) == 3
+    assert abs(O.collision_rate(codes) - 0.5) < 1e-12
+    assert json.loads(O.index_json(codes[:1])) == {"0": ["<a_1>", "<b_2>", "<c_3>", "<d_4>"]}
