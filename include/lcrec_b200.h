@@ -1,0 +1,157 @@
+/* lcrec_b200 - C ABI of the B200-native LC-Rec item-indexing hot path.
+ *
+ * The reference (jiaozihao18/LC-Rec, index/) is pure Python on torch; it has no FFI of its own.
+ * This header is the boundary a maintainer binds with ctypes: every entry
+ * point names the reference code it replaces.  All pointers are BORROWED.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Device pointers unless a name
+ * ends in `_host`.  Return value: 0 = LCREC_OK, otherwise an LCREC_ERR_* code; the text of the
+ * last error on the calling thread is available from lcrec_last_error().  There is no CPU
+ * fallback anywhere: on a machine without an sm_100 device every compute call fails with
+ * LCREC_ERR_CUDA / LCREC_ERR_UNSUPPORTED.
+ */
+#ifndef LCREC_B200_H
+#define LCREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCREC_OK 0
+#define LCREC_ERR_ARG 1          /* bad argument (NULL, size, alignment)            */
+#define LCREC_ERR_CUDA 2         /* CUDA runtime / driver error                      */
+#define LCREC_ERR_UNSUPPORTED 3  /* shape or device outside what the kernels cover   */
+#define LCREC_ERR_NOMEM 4        /* workspace too small / allocation failure         */
+#define LCREC_ERR_NUMERIC 5      /* reference `assert amplitude > 0` (vq.py:59) etc. */
+
+#define LCREC_MAX_LEVELS 8
+
+/* ---- library ------------------------------------------------------------------------- */
+int lcrec_version(void);
+const char* lcrec_strerror(int code);
+const char* lcrec_last_error(void);
+/* LCREC_OK iff the current CUDA device is compute capability 10.x (B200). */
+int lcrec_device_check(void);
+
+/* ---- a2: MLPLayers.forward (index/models/layers.py:18-43) ------------------------------
+ * y = relu(x W^T + b) per layer, last layer without ReLU unless relu_last.  Eval-mode
+ * BatchNorm1d is folded into (W, b) by the caller.  fp32-accurate: every product is
+ * evaluated as 3 TF32 tcgen05 MMAs (hi*hi + lo*hi + hi*lo) with fp32 accumulation.
+ * `weights[i]` is (dims[i+1], dims[i]) row-major like nn.Linear.weight.  The handle owns
+ * split copies of the weights; call lcrec_mlp_update() after the caller changes them.
+ */
+typedef struct lcrec_mlp lcrec_mlp_t;
+int lcrec_mlp_create(int n_layers, const int32_t* dims, const float* const* weights,
+                     const float* const* biases, int relu_last, void* stream, lcrec_mlp_t** out);
+int lcrec_mlp_update(lcrec_mlp_t* mlp, const float* const* weights, const float* const* biases,
+                     void* stream);
+int lcrec_mlp_destroy(lcrec_mlp_t* mlp);
+int64_t lcrec_mlp_workspace_bytes(const lcrec_mlp_t* mlp, int64_t n_rows);
+/* acts (nullable): n_layers device pointers receiving the fp32 output of every layer
+ * (acts[n_layers-1] may alias y).  Used by the training path to keep activations. */
+int lcrec_mlp_forward(lcrec_mlp_t* mlp, const float* x, int64_t n_rows, float* y,
+                      float* const* acts, void* workspace, int64_t workspace_bytes, void* stream);
+/* accumulation chunk: number of K elements accumulated inside TMEM before the partial sum is
+ * folded into fp32 registers with round-to-nearest (0 = whole K in TMEM). */
+int lcrec_mlp_set_acc_chunk(lcrec_mlp_t* mlp, int k_elems);
+/* tile variant for experiments: 0 = default (N tile 256: K block 16 x 4 stages), 1 = K block 32 x 2 stages */
+int lcrec_mlp_set_variant(lcrec_mlp_t* mlp, int variant);
+int lcrec_mlp_in_dim(const lcrec_mlp_t* mlp);
+int lcrec_mlp_out_dim(const lcrec_mlp_t* mlp);
+/* One nn.Linear (+ReLU) on raw fp32 operands (layers.py:23): splits x and w on the fly into ws. */
+int64_t lcrec_linear_workspace_bytes(int64_t n_rows, int k_in, int n_out);
+int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* w, const float* b,
+                         int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,
+                         int64_t ws_bytes, void* stream);
+
+/* ---- a3/a4/a7/a9: ResidualVectorQuantizer.forward, argmin branch ------------------------
+ * (index/models/rq.py:39-56, vq.py:63-75,87-99).  One fused pass over all L levels:
+ * d = (|r|^2 + |c|^2) - 2 r.c in fp32, lowest-index argmin, x_res = r + (q - r), r -= x_res.
+ * codebooks: L device pointers to (n_codes[l], e_dim) fp32.  Nullable outputs:
+ *   codes       (n, L) int64      xq  (n, e_dim) fp32 sum of x_res
+ *   resid_last  (n, e_dim) fp32   residual ENTERING level `resid_level` (for the Sinkhorn pass)
+ *   sq_err      (L) fp64          sum over rows and dims of (q - r)^2 per level (losses)
+ * n_levels_run <= L lets the caller stop before a Sinkhorn level.
+ */
+int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_levels, const float* const* codebooks,
+                      const int32_t* n_codes, int n_levels_run, int resid_level, int64_t* codes,
+                      float* xq, float* resid_last, double* sq_err, void* stream);
+
+/* ---- a4: distances only (index/models/vq.py:71-73), (n, K) fp32 ------------------------ */
+int lcrec_vq_distances(const float* r, int64_t n, int e_dim, const float* codebook, int n_codes,
+                       float* d, void* stream);
+
+/* ---- a5+a6+a7: Sinkhorn assignment -------------------------------------------------------
+ * lcrec_sinkhorn_dense: drop-in for sinkhorn_algorithm(distances, epsilon, iters)
+ * (index/models/layers.py:85-108) on an fp64 (B, K) matrix; q may alias distances.
+ * ws: workspace of lcrec_sinkhorn_workspace_bytes(B, K).  If argmax != NULL also writes
+ * torch.argmax(Q, -1) (vq.py:83, lowest index on ties, NaN counts as maximum).
+ * flags (nullable, 1 int32): bit0 = NaN/Inf seen in Q (vq.py:81).
+ */
+int64_t lcrec_sinkhorn_workspace_bytes(int64_t n_rows, int n_codes);
+int lcrec_sinkhorn_dense(const double* distances, int64_t n_rows, int n_codes, double epsilon,
+                         int iters, double* q, int64_t* argmax, int32_t* flags, void* ws,
+                         int64_t ws_bytes, void* stream);
+/* center_distance_for_constraint (vq.py:51-61): fp32 in, centred fp64 out (the .double() of
+ * vq.py:78).  status (1 int32, device): set to 1 when amplitude <= 0. */
+int lcrec_center_distances(const float* d, int64_t n_rows, int n_codes, double* centred,
+                           int32_t* status, void* ws, int64_t ws_bytes, void* stream);
+
+/* lcrec_sinkhorn_groups: one independent Sinkhorn problem per collision group
+ * (index/generate_indices.py:116-119 -> vq.py:71-83 on the group's rows).
+ * resid: (n_items, e_dim) residuals entering the last level; group g owns rows
+ * members[offsets[g] .. offsets[g+1]).  Writes new_code[item] for every member.
+ * n_groups_dev: device int64 holding the group count (<= max_groups, the launch bound). */
+int64_t lcrec_sinkhorn_groups_workspace_bytes(int64_t max_rows, int n_codes);
+int lcrec_sinkhorn_groups(const float* resid, int e_dim, const float* codebook, int n_codes,
+                          const int64_t* offsets, const int64_t* members, const int64_t* n_groups_dev,
+                          int64_t max_groups, int64_t max_rows, double epsilon, int iters,
+                          int64_t* codes, int n_levels, int level, int32_t* flags, void* ws,
+                          int64_t ws_bytes, void* stream);
+
+/* ---- a12/a14: collision bookkeeping (generate_indices.py:18-42, trainer.py:141-150) -----
+ * Packs (n, L) int64 codes into u64 keys, radix-sorts (key, item) and emits collision groups
+ * in CSR form: groups ordered by key, members ascending (the reference orders groups by
+ * first occurrence; groups are disjoint so the order does not change any result).
+ * counts (device, 4 int64): [n_unique, n_groups, n_colliding_rows, max_multiplicity].
+ */
+int64_t lcrec_collisions_workspace_bytes(int64_t n);
+int lcrec_collisions(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes,
+                     int64_t* offsets /* n+1 */, int64_t* members /* n */, int64_t* counts,
+                     void* ws, int64_t ws_bytes, void* stream);
+/* sorted (key, item) pairs only; keys_out/items_out (n) */
+int lcrec_sort_codes(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes,
+                     uint64_t* keys_out, uint32_t* items_out, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- a15: whole index generation, HOST buffers (index/generate_indices.py:85-128) -------
+ * x_host: (n, dims[0]) fp32 in pageable or pinned host memory; codes_host: (n, L) int64.
+ * Streams the embeddings to the device in chunks, PASS 0 argmin, then up to max_rounds
+ * collision rounds with per-group Sinkhorn on the last level.  stats_host (nullable, 8 int64):
+ * [rounds_run, n_unique_final, groups_round1, rows_round1, total_sinkhorn_rows, max_multiplicity,
+ *  nan_flag, 0].
+ */
+typedef struct lcrec_indexer lcrec_indexer_t;
+int lcrec_indexer_create(lcrec_mlp_t* encoder, int e_dim, int n_levels, const float* const* codebooks,
+                         const int32_t* n_codes, double last_epsilon, int sk_iters,
+                         int64_t max_items, int64_t chunk_rows, lcrec_indexer_t** out);
+int lcrec_indexer_destroy(lcrec_indexer_t* ix);
+/* device-resident input */
+int lcrec_indexer_run_device(lcrec_indexer_t* ix, const float* x, int64_t n, int max_rounds,
+                             int64_t* codes, int64_t* stats_host, void* stream);
+/* host-resident input and output */
+int lcrec_indexer_run_host(lcrec_indexer_t* ix, const float* x_host, int64_t n, int max_rounds,
+                           int64_t* codes_host, int64_t* stats_host, void* stream);
+/* building blocks of the loop, for multi-GPU drivers and tests */
+int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t n, int64_t row_offset, void* stream);
+int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* counts_host, void* stream);
+int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
+float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */
+/* number of kernels this library has launched on the calling process so far */
+int64_t lcrec_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCREC_B200_H */

@@ -1,0 +1,98 @@
+"""ctypes binding of liblcrec_b200.so (the C ABI declared in include/lcrec_b200.h).
+
+No CPU fallback: if the library is missing or the device is not an sm_100 GPU, every operator
+raises.  Build the library with ``python -m lcrec_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblcrec_b200.so")
+
+i32, i64, f64 = C.c_int32, C.c_int64, C.c_double
+vp = C.c_void_p
+pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/lcrec_b200.h one to one
+SIGNATURES = {
+    "lcrec_version": (C.c_int, []),
+    "lcrec_strerror": (C.c_char_p, [C.c_int]),
+    "lcrec_last_error": (C.c_char_p, []),
+    "lcrec_device_check": (C.c_int, []),
+    "lcrec_launch_count": (i64, []),
+    "lcrec_mlp_create": (C.c_int, [C.c_int, C.POINTER(i32), pp, pp, C.c_int, vp, pp]),
+    "lcrec_mlp_update": (C.c_int, [vp, pp, pp, vp]),
+    "lcrec_mlp_destroy": (C.c_int, [vp]),
+    "lcrec_mlp_workspace_bytes": (i64, [vp, i64]),
+    "lcrec_mlp_forward": (C.c_int, [vp, vp, i64, vp, pp, vp, i64, vp]),
+    "lcrec_mlp_set_acc_chunk": (C.c_int, [vp, C.c_int]),
+    "lcrec_mlp_set_variant": (C.c_int, [vp, C.c_int]),
+    "lcrec_mlp_in_dim": (C.c_int, [vp]),
+    "lcrec_mlp_out_dim": (C.c_int, [vp]),
+    "lcrec_linear_workspace_bytes": (i64, [i64, C.c_int, C.c_int]),
+    "lcrec_linear_forward": (C.c_int, [vp, i64, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, i64, vp]),
+    "lcrec_rq_quantize": (C.c_int, [vp, i64, C.c_int, C.c_int, pp, C.POINTER(i32), C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+    "lcrec_vq_distances": (C.c_int, [vp, i64, C.c_int, vp, C.c_int, vp, vp]),
+    "lcrec_sinkhorn_workspace_bytes": (i64, [i64, C.c_int]),
+    "lcrec_sinkhorn_dense": (C.c_int, [vp, i64, C.c_int, f64, C.c_int, vp, vp, vp, vp, i64, vp]),
+    "lcrec_center_distances": (C.c_int, [vp, i64, C.c_int, vp, vp, vp, i64, vp]),
+    "lcrec_sinkhorn_groups_workspace_bytes": (i64, [i64, C.c_int]),
+    "lcrec_sinkhorn_groups": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, f64, C.c_int, vp, C.c_int,
+                                        C.c_int, vp, vp, i64, vp]),
+    "lcrec_collisions_workspace_bytes": (i64, [i64]),
+    "lcrec_collisions": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, vp, i64, vp]),
+    "lcrec_sort_codes": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, i64, vp]),
+    "lcrec_indexer_create": (C.c_int, [vp, C.c_int, C.c_int, pp, C.POINTER(i32), f64, C.c_int, i64, i64, pp]),
+    "lcrec_indexer_destroy": (C.c_int, [vp]),
+    "lcrec_indexer_run_device": (C.c_int, [vp, vp, i64, C.c_int, vp, C.POINTER(i64), vp]),
+    "lcrec_indexer_run_host": (C.c_int, [vp, vp, i64, C.c_int, vp, C.POINTER(i64), vp]),
+    "lcrec_indexer_pass0": (C.c_int, [vp, vp, i64, i64, vp]),
+    "lcrec_indexer_round": (C.c_int, [vp, i64, C.POINTER(i64), vp]),
+    "lcrec_indexer_codes": (vp, [vp]),
+    "lcrec_indexer_resid": (vp, [vp]),
+}
+
+_lib = None
+
+
+class LcrecError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"lcrec_b200 error {code}: {message}")
+        self.code = code
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(python -m lcrec_b200.build).  lcrec_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        lib = load()
+        detail = lib.lcrec_last_error().decode(errors="replace")
+        kind = lib.lcrec_strerror(rc).decode()
+        raise LcrecError(rc, f"{kind}: {detail}")
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(p) for p in ptrs])
+    return arr
+
+
+def i32_array(vals):
+    return (i32 * len(vals))(*[int(v) for v in vals])

@@ -1,0 +1,261 @@
+// Library-level entry points and the index-generation driver (C ABI).
+//
+// lcrec_indexer_* restates the main body of the reference script index/generate_indices.py:85-128
+// on the device: PASS 0 = encoder + fused argmin residual quantisation for all items (chunked so
+// that 10 M x 4096 fp32 inputs can be streamed), then up to `max_rounds` collision rounds, each =
+// sort/unique on packed codes -> per-group Sinkhorn on the last level -> overwrite the last code.
+// The reference re-runs the encoder on every group every round; the latents are the same numbers
+// (up to GEMM batch-shape rounding), so PASS 0 keeps the residual entering the last
+// level (128 B/item) and the rounds never touch the 16 KB/item embeddings again.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace lcrec {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sms = v;
+    else
+      return 148;
+  }
+  return sms;
+}
+
+}  // namespace lcrec
+
+using namespace lcrec;
+
+extern "C" int lcrec_version(void) { return 100; }
+
+extern "C" const char* lcrec_strerror(int code) {
+  switch (code) {
+    case LCREC_OK: return "ok";
+    case LCREC_ERR_ARG: return "invalid argument";
+    case LCREC_ERR_CUDA: return "CUDA error";
+    case LCREC_ERR_UNSUPPORTED: return "unsupported shape or device";
+    case LCREC_ERR_NOMEM: return "workspace too small or out of memory";
+    case LCREC_ERR_NUMERIC: return "numeric guard failed";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* lcrec_last_error(void) { return g_err; }
+
+extern "C" int64_t lcrec_launch_count(void) { return g_launches.load(); }
+
+extern "C" int lcrec_device_check(void) {
+  static int cached = -1;
+  if (cached == LCREC_OK) return LCREC_OK;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); cudaGetLastError(); return LCREC_ERR_CUDA; }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) { set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); cudaGetLastError(); return LCREC_ERR_CUDA; }
+  if (major != 10) { set_error("device compute capability %d.x is not sm_100 (B200); kernels are built for sm_100a only", major); return LCREC_ERR_UNSUPPORTED; }
+  cached = LCREC_OK;
+  return LCREC_OK;
+}
+
+// ====================================================================== indexer
+struct lcrec_indexer {
+  lcrec_mlp_t* enc = nullptr;
+  int in_dim = 0, D = 0, L = 0;
+  std::vector<const float*> cb;
+  std::vector<int32_t> K;
+  double eps = 0.003; int iters = 50;
+  int64_t max_items = 0, chunk_rows = 0;
+  int64_t* codes = nullptr; float* resid = nullptr; float* z = nullptr;
+  void* mlp_ws = nullptr; int64_t mlp_ws_bytes = 0;
+  int64_t* offsets = nullptr; int64_t* members = nullptr; int64_t* counts = nullptr; int32_t* flags = nullptr;
+  void* col_ws = nullptr; int64_t col_ws_bytes = 0;
+  void* sk_ws = nullptr; int64_t sk_ws_bytes = 0;
+  float* stage[2] = {nullptr, nullptr};
+  int64_t* counts_host = nullptr;   // pinned: 4 counts + flags
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+};
+
+extern "C" int lcrec_mlp_in_dim(const lcrec_mlp_t* m);
+extern "C" int lcrec_mlp_out_dim(const lcrec_mlp_t* m);
+
+#define IX_ALLOC(ptr, bytes)                                                                     \
+  do {                                                                                           \
+    if (cudaMalloc((void**)&(ptr), (size_t)(bytes)) != cudaSuccess) {                            \
+      set_error("indexer: cudaMalloc(%lld) failed: %s", (long long)(bytes), cudaGetErrorString(cudaGetLastError())); \
+      lcrec_indexer_destroy(ix);                                                                 \
+      return LCREC_ERR_NOMEM;                                                                    \
+    }                                                                                            \
+  } while (0)
+
+extern "C" int lcrec_indexer_create(lcrec_mlp_t* encoder, int e_dim, int n_levels, const float* const* codebooks,
+                                    const int32_t* n_codes, double last_epsilon, int sk_iters, int64_t max_items,
+                                    int64_t chunk_rows, lcrec_indexer_t** out) {
+  LC_ARG(encoder && e_dim > 0 && n_levels >= 1 && n_levels <= LCREC_MAX_LEVELS && codebooks && n_codes && out);
+  LC_ARG(max_items > 0 && chunk_rows > 0 && last_epsilon > 0.0 && sk_iters >= 0);
+  LC_ARG(lcrec_mlp_out_dim(encoder) == e_dim);
+  LC_TRY(lcrec_device_check());
+  lcrec_indexer* ix = new lcrec_indexer();
+  ix->enc = encoder; ix->in_dim = lcrec_mlp_in_dim(encoder); ix->D = e_dim; ix->L = n_levels;
+  ix->cb.assign(codebooks, codebooks + n_levels); ix->K.assign(n_codes, n_codes + n_levels);
+  ix->eps = last_epsilon; ix->iters = sk_iters; ix->max_items = max_items;
+  ix->chunk_rows = std::min(chunk_rows, max_items);
+  IX_ALLOC(ix->codes, sizeof(int64_t) * max_items * n_levels);
+  IX_ALLOC(ix->resid, sizeof(float) * max_items * e_dim);
+  IX_ALLOC(ix->z, sizeof(float) * ix->chunk_rows * e_dim);
+  ix->mlp_ws_bytes = lcrec_mlp_workspace_bytes(encoder, ix->chunk_rows);
+  IX_ALLOC(ix->mlp_ws, ix->mlp_ws_bytes);
+  IX_ALLOC(ix->offsets, sizeof(int64_t) * (max_items + 1));
+  IX_ALLOC(ix->members, sizeof(int64_t) * max_items);
+  IX_ALLOC(ix->counts, sizeof(int64_t) * 8);
+  ix->flags = reinterpret_cast<int32_t*>(ix->counts + 4);
+  ix->col_ws_bytes = lcrec_collisions_workspace_bytes(max_items);
+  IX_ALLOC(ix->col_ws, ix->col_ws_bytes);
+  ix->sk_ws_bytes = lcrec_sinkhorn_groups_workspace_bytes(max_items, n_codes[n_levels - 1]);
+  IX_ALLOC(ix->sk_ws, ix->sk_ws_bytes);
+  if (cudaMallocHost((void**)&ix->counts_host, sizeof(int64_t) * 8) != cudaSuccess) {
+    set_error("indexer: cudaMallocHost failed"); lcrec_indexer_destroy(ix); return LCREC_ERR_NOMEM;
+  }
+  *out = ix;
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_indexer_destroy(lcrec_indexer_t* ix) {
+  if (!ix) return LCREC_OK;
+  cudaFree(ix->codes); cudaFree(ix->resid); cudaFree(ix->z); cudaFree(ix->mlp_ws); cudaFree(ix->offsets);
+  cudaFree(ix->members); cudaFree(ix->counts); cudaFree(ix->col_ws); cudaFree(ix->sk_ws);
+  cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
+  if (ix->counts_host) cudaFreeHost(ix->counts_host);
+  for (int i = 0; i < 2; ++i) { if (ix->ev_copied[i]) cudaEventDestroy(ix->ev_copied[i]); if (ix->ev_consumed[i]) cudaEventDestroy(ix->ev_consumed[i]); }
+  if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
+  delete ix;
+  return LCREC_OK;
+}
+
+extern "C" int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix) { return ix ? ix->codes : nullptr; }
+extern "C" float* lcrec_indexer_resid(lcrec_indexer_t* ix) { return ix ? ix->resid : nullptr; }
+
+// PASS 0 for rows [row_offset, row_offset + n) (generate_indices.py:85-95)
+extern "C" int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t n, int64_t row_offset, void* stream) {
+  LC_ARG(ix && n >= 0 && row_offset >= 0 && row_offset + n <= ix->max_items);
+  if (n == 0) return LCREC_OK;
+  LC_ARG(x != nullptr);
+  for (int64_t s = 0; s < n; s += ix->chunk_rows) {
+    const int64_t m = std::min(ix->chunk_rows, n - s);
+    LC_TRY(lcrec_mlp_forward(ix->enc, x + s * ix->in_dim, m, ix->z, nullptr, ix->mlp_ws, ix->mlp_ws_bytes, stream));
+    LC_TRY(lcrec_rq_quantize(ix->z, m, ix->D, ix->L, ix->cb.data(), ix->K.data(), ix->L, ix->L - 1,
+                             ix->codes + (row_offset + s) * ix->L, nullptr, ix->resid + (row_offset + s) * ix->D,
+                             nullptr, stream));
+  }
+  return LCREC_OK;
+}
+
+// One check (+ resolve when `resolve`): counts_host receives [n_unique, n_groups, rows, max_mult, flags]
+static int indexer_check(lcrec_indexer_t* ix, int64_t n, bool resolve, int64_t* counts_host, cudaStream_t st) {
+  LC_TRY(lcrec_collisions(ix->codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
+                          ix->col_ws_bytes, st));
+  LC_CUDA(cudaMemsetAsync(ix->flags, 0, sizeof(int32_t) * 2, st));
+  LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 5, cudaMemcpyDeviceToHost, st));
+  LC_CUDA(cudaStreamSynchronize(st));
+  const int64_t groups = ix->counts_host[1], rows = ix->counts_host[2];
+  if (resolve && groups > 0) {
+    LC_TRY(lcrec_sinkhorn_groups(ix->resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
+                                 ix->counts + 1, groups, rows, ix->eps, ix->iters, ix->codes, ix->L, ix->L - 1,
+                                 ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));
+  }
+  if (counts_host) memcpy(counts_host, ix->counts_host, sizeof(int64_t) * 4);
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* counts_host, void* stream) {
+  LC_ARG(ix && n >= 0 && n <= ix->max_items);
+  return indexer_check(ix, n, true, counts_host, (cudaStream_t)stream);
+}
+
+static int indexer_rounds(lcrec_indexer_t* ix, int64_t n, int max_rounds, int64_t* stats, cudaStream_t st) {
+  int64_t c[4] = {0, 0, 0, 0};
+  int64_t rounds = 0, g1 = 0, r1 = 0, tot_rows = 0;
+  int32_t flags_acc = 0;
+  while (true) {                                     // generate_indices.py:108-128
+    const bool resolve = rounds < max_rounds;
+    LC_TRY(indexer_check(ix, n, resolve, c, st));
+    if (c[0] == n || !resolve) break;
+    if (rounds == 0) { g1 = c[1]; r1 = c[2]; }
+    tot_rows += c[2];
+    ++rounds;
+    int32_t f[2];
+    LC_CUDA(cudaMemcpyAsync(f, ix->flags, sizeof(f), cudaMemcpyDeviceToHost, st));
+    LC_CUDA(cudaStreamSynchronize(st));
+    flags_acc |= f[0];
+    if (f[0] & 2) { set_error("indexer: workspace for oversized collision groups exhausted"); return LCREC_ERR_NOMEM; }
+    if (f[0] & 4) { set_error("indexer: amplitude > 0 failed (vq.py:59)"); return LCREC_ERR_NUMERIC; }
+  }
+  if (stats) {
+    stats[0] = rounds; stats[1] = c[0]; stats[2] = g1; stats[3] = r1; stats[4] = tot_rows; stats[5] = c[3];
+    stats[6] = flags_acc & 1; stats[7] = 0;
+  }
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_indexer_run_device(lcrec_indexer_t* ix, const float* x, int64_t n, int max_rounds, int64_t* codes,
+                                        int64_t* stats_host, void* stream) {
+  LC_ARG(ix && n >= 0 && n <= ix->max_items && max_rounds >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { if (stats_host) memset(stats_host, 0, 8 * sizeof(int64_t)); return LCREC_OK; }
+  LC_TRY(lcrec_indexer_pass0(ix, x, n, 0, stream));
+  LC_TRY(indexer_rounds(ix, n, max_rounds, stats_host, st));
+  if (codes && codes != ix->codes)
+    LC_CUDA(cudaMemcpyAsync(codes, ix->codes, sizeof(int64_t) * n * ix->L, cudaMemcpyDeviceToDevice, st));
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_indexer_run_host(lcrec_indexer_t* ix, const float* x_host, int64_t n, int max_rounds,
+                                      int64_t* codes_host, int64_t* stats_host, void* stream) {
+  LC_ARG(ix && n >= 0 && n <= ix->max_items && max_rounds >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { if (stats_host) memset(stats_host, 0, 8 * sizeof(int64_t)); return LCREC_OK; }
+  LC_ARG(x_host && codes_host);
+  if (!ix->copy_stream) {
+    LC_CUDA(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      LC_CUDA(cudaEventCreateWithFlags(&ix->ev_copied[i], cudaEventDisableTiming));
+      LC_CUDA(cudaEventCreateWithFlags(&ix->ev_consumed[i], cudaEventDisableTiming));
+      LC_CUDA(cudaMalloc((void**)&ix->stage[i], sizeof(float) * ix->chunk_rows * ix->in_dim));
+    }
+  }
+  // double-buffered H2D on the copy stream, compute on `st`
+  const int64_t nchunks = ceil_div(n, ix->chunk_rows);
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = (int)(c & 1);
+    const int64_t s = c * ix->chunk_rows, m = std::min(ix->chunk_rows, n - s);
+    if (c >= 2) LC_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->ev_consumed[b], 0));
+    LC_CUDA(cudaMemcpyAsync(ix->stage[b], x_host + s * ix->in_dim, sizeof(float) * m * ix->in_dim,
+                            cudaMemcpyHostToDevice, ix->copy_stream));
+    LC_CUDA(cudaEventRecord(ix->ev_copied[b], ix->copy_stream));
+    LC_CUDA(cudaStreamWaitEvent(st, ix->ev_copied[b], 0));
+    LC_TRY(lcrec_indexer_pass0(ix, ix->stage[b], m, s, stream));
+    LC_CUDA(cudaEventRecord(ix->ev_consumed[b], st));
+  }
+  LC_TRY(indexer_rounds(ix, n, max_rounds, stats_host, st));
+  LC_CUDA(cudaMemcpyAsync(codes_host, ix->codes, sizeof(int64_t) * n * ix->L, cudaMemcpyDeviceToHost, st));
+  LC_CUDA(cudaStreamSynchronize(st));
+  return LCREC_OK;
+}

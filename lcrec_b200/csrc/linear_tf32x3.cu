@@ -1,0 +1,513 @@
+// fp32-accurate Linear(+bias, +ReLU) on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// Replaces nn.Linear + ReLU inside MLPLayers.forward (reference index/models/layers.py:22-43).
+// The reference computes in IEEE fp32; bf16 or single-pass TF32 change 11 % / 1.2 % of the
+// emitted codes, so every product is evaluated with the 3xTF32 split
+//     x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo,   x_hi = tf32(x), x_lo = tf32(x - x_hi)
+// which carries ~22 mantissa bits per operand.  Operands arrive pre-split (A_hi/A_lo from
+// split_tf32_kernel or from the previous layer's epilogue, W_hi/W_lo prepared once per
+// checkpoint), are staged by TMA into 128B/64B-swizzled shared memory, and one elected thread
+// issues tcgen05.mma.kind::tf32 into a TMEM accumulator.
+//
+// Accumulation accuracy: the tensor core adds into an fp32 TMEM accumulator; to keep the
+// rounding error of a K=4096 reduction at fp32-SIMT level the K loop can be cut into chunks
+// (`chunk_kblocks`): each chunk accumulates in one of two TMEM buffers and the epilogue warps
+// fold finished chunks into fp32 registers with round-to-nearest adds while the next chunk is
+// being multiplied (two TMEM buffers = the chunks ping-pong).
+//
+// CTA = 10 warps: warps 0-7 fold/epilogue (TMEM -> registers -> bias/ReLU/split -> global),
+// warp 8 = TMA producer (one lane), warp 9 = TMEM allocator + MMA issuer (one lane).
+// Tile: 128 rows x BN columns, K block = BK fp32 (BK*4 bytes = swizzle span).
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lcrec {
+
+using namespace ptx;
+
+struct LinearArgs {
+  int64_t n_rows;     // M
+  int n_out;          // N
+  int num_kblocks;    // ceil(K / BK)
+  int chunk_kblocks;  // K blocks per TMEM accumulation chunk (>= 1)
+  int relu;
+  const float* bias;  // (n_out) or null
+  float* y;           // (n_rows, ldy) fp32 or null
+  int64_t ldy;
+  float* y_hi;        // split output for the next layer, or null
+  float* y_lo;
+  int64_t ld_split;
+};
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 320;
+
+template <int BN, int BK, int STAGES>
+struct LinearCfg {
+  static constexpr int A_BYTES = kTileM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t ROW_BYTES = BK * 4;        // 128 or 64
+  static constexpr uint32_t SBO = 8 * ROW_BYTES;
+  static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? 2u : (ROW_BYTES == 64 ? 4u : 6u);
+  static_assert(BK == 32 || BK == 16, "BK*4 must be a 128B or 64B swizzle span");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                     const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                     const LinearArgs args, const int tiles_n) {
+  using C = LinearCfg<BN, BK, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const uint32_t bar0 = base + STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(smem + STAGES * C::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x % tiles_n;
+  const int64_t tile_m = blockIdx.x / tiles_n;
+  const int nkb = args.num_kblocks;
+  const int ckb = args.chunk_kblocks;
+  const int nchunks = (nkb + ckb - 1) / ckb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    prefetch_tensormap(&map_ahi); prefetch_tensormap(&map_alo);
+    prefetch_tensormap(&map_bhi); prefetch_tensormap(&map_blo);
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const int row0 = (int)(tile_m * kTileM);
+      const int col0 = tile_n * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+        const uint32_t dst = base + s * C::STAGE_BYTES;
+        tma_load_2d(dst, &map_ahi, full_bar(s), kb * BK, row0);
+        tma_load_2d(dst + C::A_BYTES, &map_alo, full_bar(s), kb * BK, row0);
+        tma_load_2d(dst + 2 * C::A_BYTES, &map_bhi, full_bar(s), kb * BK, col0);
+        tma_load_2d(dst + 2 * C::A_BYTES + C::B_BYTES, &map_blo, full_bar(s), kb * BK, col0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(kTileM, BN, 2);
+      int kb = 0;
+      for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(tempty_bar(b), (((uint32_t)c >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+        const int kb_end = min(nkb, kb + ckb);
+        bool first = true;
+        for (; kb < kb_end; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t a_hi = base + s * C::STAGE_BYTES;
+          const uint64_t d_ahi = umma_smem_desc(a_hi, C::SBO, C::LAYOUT);
+          const uint64_t d_alo = umma_smem_desc(a_hi + C::A_BYTES, C::SBO, C::LAYOUT);
+          const uint64_t d_bhi = umma_smem_desc(a_hi + 2 * C::A_BYTES, C::SBO, C::LAYOUT);
+          const uint64_t d_blo = umma_smem_desc(a_hi + 2 * C::A_BYTES + C::B_BYTES, C::SBO, C::LAYOUT);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes along K
+            // small cross terms first, then the dominant hi*hi product
+            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, first ? 0u : 1u);
+            umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+            umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            first = false;
+          }
+          umma_commit(empty_bar(s));   // smem slot reusable once these MMAs have read it
+        }
+        umma_commit(tfull_bar(b));     // chunk complete in TMEM
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ fold + epilogue warps
+    constexpr int NCOL = BN / 2;
+    constexpr int LDW = NCOL >= 32 ? 32 : 16;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = warp >> 2;    // column half
+    float acc[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) acc[i] = 0.f;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NCOL);
+    for (int c = 0; c < nchunks; ++c) {
+      const int b = c & 1;
+      mbar_wait(tfull_bar(b), ((uint32_t)c >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < NCOL; j += LDW) {
+        uint32_t v[LDW];
+        if constexpr (LDW == 32) tmem_ld32(t_lane + (uint32_t)(b * BN + j), v);
+        else tmem_ld16(t_lane + (uint32_t)(b * BN + j), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < LDW; ++i) acc[j + i] += __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(b));
+    }
+    // epilogue: bias, ReLU, optional 3xTF32 split for the next layer
+    const int64_t row = tile_m * kTileM + q * 32 + lane;
+    const int col_base = tile_n * BN + half * NCOL;
+    if (row < args.n_rows) {
+#pragma unroll
+      for (int j = 0; j < NCOL; j += 4) {
+        const int col = col_base + j;
+        if (col >= args.n_out) break;
+        float v[4], hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float t = acc[j + i];
+          if (args.bias != nullptr && col + i < args.n_out) t += __ldg(args.bias + col + i);
+          if (args.relu) t = fmaxf(t, 0.f);
+          v[i] = t;
+          hi[i] = to_tf32(t);
+          lo[i] = to_tf32(t - hi[i]);
+        }
+        if (col + 3 < args.n_out) {
+          if (args.y) *reinterpret_cast<float4*>(args.y + row * args.ldy + col) = make_float4(v[0], v[1], v[2], v[3]);
+          if (args.y_hi) {
+            *reinterpret_cast<float4*>(args.y_hi + row * args.ld_split + col) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(args.y_lo + row * args.ld_split + col) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        } else {
+          for (int i = 0; i < 4 && col + i < args.n_out; ++i) {
+            if (args.y) args.y[row * args.ldy + col + i] = v[i];
+            if (args.y_hi) { args.y_hi[row * args.ld_split + col + i] = hi[i]; args.y_lo[row * args.ld_split + col + i] = lo[i]; }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// x -> (hi, lo) with hi = tf32(x), lo = tf32(x - hi); pads columns [k, ld_out) with zeros.
+__global__ void split_tf32_kernel(const float* __restrict__ x, int64_t rows, int k, int64_t ldx,
+                                  float* __restrict__ hi, float* __restrict__ lo, int64_t ld_out) {
+  const int64_t groups_per_row = ld_out >> 2;
+  const int64_t total = rows * groups_per_row;
+  const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total;
+       g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = g / groups_per_row;
+    const int c = (int)(g - r * groups_per_row) << 2;
+    float v[4];
+    if (vec_ok && c + 3 < k) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(x + r * ldx + c));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (c + i < k) ? x[r * ldx + c + i] : 0.f;
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = to_tf32(v[i]); l[i] = to_tf32(v[i] - h[i]); }
+    *reinterpret_cast<float4*>(hi + r * ld_out + c) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo + r * ld_out + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// fp32 row-major (rows, k) matrix with row stride ld; box = (bk, box_rows); OOB reads give zeros.
+static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int k, int64_t ld, int bk, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return LCREC_ERR_CUDA; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3)) {
+    set_error("TMA operand must be 16-byte aligned with a row stride multiple of 4 floats");
+    return LCREC_ERR_ARG;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = bk * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld k %d ld %lld)", (int)r, (long long)rows, k, (long long)ld); return LCREC_ERR_CUDA; }
+  return LCREC_OK;
+}
+
+struct LinearProblem {
+  const float *a_hi, *a_lo; int64_t n_rows; int k; int64_t lda;
+  const float *w_hi, *w_lo; int n_out; int64_t ldw;
+  const float* bias; int relu;
+  float* y; int64_t ldy; float *y_hi, *y_lo; int64_t ld_split;
+  int acc_chunk;   // K elements per TMEM chunk, 0 = all
+  int variant;     // 0 = default tile choice; 1 = force BK=32 two-stage for BN=256
+};
+
+template <int BN, int BK, int STAGES>
+static int launch_cfg(const LinearProblem& p, cudaStream_t st) {
+  using C = LinearCfg<BN, BK, STAGES>;
+  static bool attr_set = false;
+  auto kern = linear_tf32x3_kernel<BN, BK, STAGES>;
+  if (!attr_set) {
+    LC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  LC_TRY(make_map(&ma_hi, p.a_hi, p.n_rows, p.k, p.lda, BK, kTileM));
+  LC_TRY(make_map(&ma_lo, p.a_lo, p.n_rows, p.k, p.lda, BK, kTileM));
+  LC_TRY(make_map(&mb_hi, p.w_hi, p.n_out, p.k, p.ldw, BK, BN));
+  LC_TRY(make_map(&mb_lo, p.w_lo, p.n_out, p.k, p.ldw, BK, BN));
+  LinearArgs a;
+  a.n_rows = p.n_rows; a.n_out = p.n_out;
+  a.num_kblocks = (int)ceil_div(p.k, BK);
+  a.chunk_kblocks = p.acc_chunk <= 0 ? a.num_kblocks : (int)std::max<int64_t>(1, p.acc_chunk / BK);
+  a.relu = p.relu; a.bias = p.bias; a.y = p.y; a.ldy = p.ldy; a.y_hi = p.y_hi; a.y_lo = p.y_lo; a.ld_split = p.ld_split;
+  const int tiles_n = (int)ceil_div(p.n_out, BN);
+  const int64_t tiles_m = ceil_div(p.n_rows, kTileM);
+  const int64_t grid = tiles_m * tiles_n;
+  if (grid <= 0 || grid > 0x7fffffffLL) { set_error("linear: grid %lld out of range", (long long)grid); return LCREC_ERR_ARG; }
+  kern<<<(unsigned)grid, kThreads, C::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a, tiles_n);
+  LC_LAUNCH_CHECK("linear_tf32x3_kernel");
+  return LCREC_OK;
+}
+
+int launch_linear(const LinearProblem& p, cudaStream_t st) {
+  if (p.n_rows == 0) return LCREC_OK;
+  if (p.k <= 0 || p.n_out <= 0) { set_error("linear: empty K or N"); return LCREC_ERR_ARG; }
+  if (p.n_out > 128) return p.variant == 1 ? launch_cfg<256, 32, 2>(p, st) : launch_cfg<256, 16, 4>(p, st);
+  if (p.n_out > 64) return launch_cfg<128, 32, 3>(p, st);
+  if (p.n_out > 32) return launch_cfg<64, 32, 4>(p, st);
+  return launch_cfg<32, 32, 4>(p, st);
+}
+
+int launch_split(const float* x, int64_t rows, int k, int64_t ldx, float* hi, float* lo, int64_t ld_out,
+                 cudaStream_t st) {
+  if (rows == 0) return LCREC_OK;
+  const int64_t total = rows * (ld_out / 4);
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>(ceil_div(total, threads), (int64_t)num_sms() * 16);
+  split_tf32_kernel<<<(unsigned)blocks, threads, 0, st>>>(x, rows, k, ldx, hi, lo, ld_out);
+  LC_LAUNCH_CHECK("split_tf32_kernel");
+  return LCREC_OK;
+}
+
+}  // namespace lcrec
+
+// ====================================================================== C ABI: MLP
+using namespace lcrec;
+
+struct lcrec_mlp {
+  int n_layers = 0;
+  std::vector<int> dims;
+  std::vector<float*> w_hi, w_lo, bias;   // device, owned
+  std::vector<int64_t> ldw;
+  int relu_last = 0;
+  int acc_chunk = 0;
+  int variant = 0;
+  int max_hidden_ld = 0;
+};
+
+static inline int64_t ld4(int64_t k) { return round_up(k, 4); }
+
+extern "C" int lcrec_mlp_update(lcrec_mlp_t* m, const float* const* weights, const float* const* biases,
+                                void* stream) {
+  LC_ARG(m != nullptr && weights != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < m->n_layers; ++l) {
+    LC_ARG(weights[l] != nullptr);
+    LC_TRY(launch_split(weights[l], m->dims[l + 1], m->dims[l], m->dims[l], m->w_hi[l], m->w_lo[l], m->ldw[l], st));
+    if (biases && biases[l]) {
+      LC_CUDA(cudaMemcpyAsync(m->bias[l], biases[l], sizeof(float) * m->dims[l + 1], cudaMemcpyDeviceToDevice, st));
+    } else {
+      LC_CUDA(cudaMemsetAsync(m->bias[l], 0, sizeof(float) * m->dims[l + 1], st));
+    }
+  }
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_mlp_create(int n_layers, const int32_t* dims, const float* const* weights,
+                                const float* const* biases, int relu_last, void* stream, lcrec_mlp_t** out) {
+  LC_ARG(n_layers >= 1 && n_layers <= 64 && dims && weights && out);
+  LC_TRY(lcrec_device_check());
+  lcrec_mlp* m = new lcrec_mlp();
+  m->n_layers = n_layers;
+  m->dims.assign(dims, dims + n_layers + 1);
+  m->relu_last = relu_last;
+  for (int l = 0; l <= n_layers; ++l) {
+    if (dims[l] <= 0) { delete m; set_error("mlp: non-positive dimension"); return LCREC_ERR_ARG; }
+    if (l > 0 && l < n_layers) m->max_hidden_ld = std::max<int>(m->max_hidden_ld, (int)ld4(dims[l]));
+  }
+  m->w_hi.assign(n_layers, nullptr); m->w_lo.assign(n_layers, nullptr); m->bias.assign(n_layers, nullptr);
+  m->ldw.assign(n_layers, 0);
+  for (int l = 0; l < n_layers; ++l) {
+    m->ldw[l] = ld4(dims[l]);
+    const size_t wbytes = sizeof(float) * (size_t)dims[l + 1] * m->ldw[l];
+    if (cudaMalloc(&m->w_hi[l], wbytes) != cudaSuccess || cudaMalloc(&m->w_lo[l], wbytes) != cudaSuccess ||
+        cudaMalloc(&m->bias[l], sizeof(float) * dims[l + 1]) != cudaSuccess) {
+      set_error("mlp: cudaMalloc of split weights failed: %s", cudaGetErrorString(cudaGetLastError()));
+      lcrec_mlp_destroy(m);
+      return LCREC_ERR_NOMEM;
+    }
+  }
+  int r = lcrec_mlp_update(m, weights, biases, stream);
+  if (r != LCREC_OK) { lcrec_mlp_destroy(m); return r; }
+  *out = m;
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_mlp_destroy(lcrec_mlp_t* m) {
+  if (!m) return LCREC_OK;
+  for (auto p : m->w_hi) if (p) cudaFree(p);
+  for (auto p : m->w_lo) if (p) cudaFree(p);
+  for (auto p : m->bias) if (p) cudaFree(p);
+  delete m;
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_mlp_set_acc_chunk(lcrec_mlp_t* m, int k_elems) {
+  LC_ARG(m != nullptr && k_elems >= 0);
+  m->acc_chunk = k_elems;
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_mlp_set_variant(lcrec_mlp_t* m, int variant) {
+  LC_ARG(m != nullptr);
+  m->variant = variant;
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_mlp_in_dim(const lcrec_mlp_t* m) { return m ? m->dims.front() : -1; }
+extern "C" int lcrec_mlp_out_dim(const lcrec_mlp_t* m) { return m ? m->dims.back() : -1; }
+
+extern "C" int64_t lcrec_mlp_workspace_bytes(const lcrec_mlp_t* m, int64_t n_rows) {
+  if (!m || n_rows < 0) return -1;
+  int64_t b = 2 * arena_need(sizeof(float) * n_rows * ld4(m->dims[0]));          // split input
+  b += 4 * arena_need(sizeof(float) * n_rows * std::max(m->max_hidden_ld, 4));  // hi/lo ping-pong
+  return b + 1024;
+}
+
+extern "C" int lcrec_mlp_forward(lcrec_mlp_t* m, const float* x, int64_t n_rows, float* y, float* const* acts,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+  LC_ARG(m != nullptr && n_rows >= 0);
+  if (n_rows == 0) return LCREC_OK;
+  LC_ARG(x != nullptr && y != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(workspace, workspace_bytes);
+  const int64_t ld0 = ld4(m->dims[0]);
+  float* in_hi = ar.take<float>(n_rows * ld0);
+  float* in_lo = ar.take<float>(n_rows * ld0);
+  const int64_t hld = std::max(m->max_hidden_ld, 4);
+  float* buf[2][2];
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) buf[i][j] = ar.take<float>(n_rows * hld);
+  if (!ar.ok()) { set_error("mlp_forward: workspace too small (%lld bytes given, %lld needed)", (long long)workspace_bytes, (long long)lcrec_mlp_workspace_bytes(m, n_rows)); return LCREC_ERR_NOMEM; }
+  LC_TRY(launch_split(x, n_rows, m->dims[0], m->dims[0], in_hi, in_lo, ld0, st));
+  const float *a_hi = in_hi, *a_lo = in_lo;
+  int64_t lda = ld0;
+  for (int l = 0; l < m->n_layers; ++l) {
+    const bool last = (l == m->n_layers - 1);
+    LinearProblem p{};
+    p.a_hi = a_hi; p.a_lo = a_lo; p.n_rows = n_rows; p.k = m->dims[l]; p.lda = lda;
+    p.w_hi = m->w_hi[l]; p.w_lo = m->w_lo[l]; p.n_out = m->dims[l + 1]; p.ldw = m->ldw[l];
+    p.bias = m->bias[l]; p.relu = last ? m->relu_last : 1;
+    p.acc_chunk = m->acc_chunk; p.variant = m->variant;
+    if (last) { p.y = y; p.ldy = m->dims[l + 1]; }
+    else {
+      p.y_hi = buf[l & 1][0]; p.y_lo = buf[l & 1][1]; p.ld_split = ld4(m->dims[l + 1]);
+      if (acts && acts[l]) { p.y = acts[l]; p.ldy = m->dims[l + 1]; }
+    }
+    if (p.ldy && ((p.ldy & 3) || (reinterpret_cast<uintptr_t>(p.y) & 15))) {
+      set_error("mlp_forward: output width %lld must be a multiple of 4 floats and 16-byte aligned", (long long)p.ldy);
+      return LCREC_ERR_UNSUPPORTED;
+    }
+    LC_TRY(launch_linear(p, st));
+    a_hi = p.y_hi; a_lo = p.y_lo; lda = p.ld_split;
+  }
+  if (acts && acts[m->n_layers - 1] && acts[m->n_layers - 1] != y)
+    LC_CUDA(cudaMemcpyAsync(acts[m->n_layers - 1], y, sizeof(float) * n_rows * m->dims[m->n_layers], cudaMemcpyDeviceToDevice, st));
+  return LCREC_OK;
+}
+
+// Single fused Linear(+bias)(+ReLU) on raw fp32 operands (splits both on the fly into `ws`).
+extern "C" int64_t lcrec_linear_workspace_bytes(int64_t n_rows, int k_in, int n_out) {
+  return 2 * arena_need(sizeof(float) * n_rows * ld4(k_in)) + 2 * arena_need(sizeof(float) * (int64_t)n_out * ld4(k_in)) + 1024;
+}
+extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* w, const float* b,
+                                    int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,
+                                    int64_t ws_bytes, void* stream) {
+  LC_ARG(x && w && y && n_rows >= 0 && k_in > 0 && n_out > 0);
+  LC_TRY(lcrec_device_check());
+  if (n_rows == 0) return LCREC_OK;
+  LC_ARG((n_out & 3) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  const int64_t ldk = ld4(k_in);
+  float* a_hi = ar.take<float>(n_rows * ldk); float* a_lo = ar.take<float>(n_rows * ldk);
+  float* w_hi = ar.take<float>((int64_t)n_out * ldk); float* w_lo = ar.take<float>((int64_t)n_out * ldk);
+  if (!ar.ok()) { set_error("linear_forward: workspace too small"); return LCREC_ERR_NOMEM; }
+  LC_TRY(launch_split(x, n_rows, k_in, k_in, a_hi, a_lo, ldk, st));
+  LC_TRY(launch_split(w, n_out, k_in, k_in, w_hi, w_lo, ldk, st));
+  LinearProblem p{};
+  p.a_hi = a_hi; p.a_lo = a_lo; p.n_rows = n_rows; p.k = k_in; p.lda = ldk;
+  p.w_hi = w_hi; p.w_lo = w_lo; p.n_out = n_out; p.ldw = ldk; p.bias = b; p.relu = relu;
+  p.y = y; p.ldy = n_out; p.acc_chunk = acc_chunk; p.variant = variant;
+  return launch_linear(p, st);
+}

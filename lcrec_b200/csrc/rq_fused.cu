@@ -1,0 +1,304 @@
+// Fused all-levels residual quantisation (argmin branch).
+//
+// Replaces the per-level torch ops of VectorQuantizer.forward (reference index/models/vq.py:63-75,
+// 87-99) chained by ResidualVectorQuantizer.forward (index/models/rq.py:39-56): for every level
+//   d_k = (|r|^2 + |c_k|^2) - 2 r.c_k        fp32, same evaluation order as vq.py:71-73
+//   idx = first argmin_k d_k                  torch.argmin tie rule
+//   x_res = r + (c_idx - r)                   straight-through forward value, vq.py:95
+//   r <- r - x_res ; x_q <- x_q + x_res       rq.py:47-48
+// One thread owns one item and keeps the residual in registers for all levels; the codebooks of
+// all levels (4 x 256 x 32 fp32 = 128 KB at the run.sh shape) and their squared norms are staged
+// once per CTA in shared memory and read as warp-wide broadcasts.  The kernel is FP32-FMA bound
+// (65 536 FLOP per 128 B read), not HBM bound.
+#include "common.cuh"
+
+namespace lcrec {
+
+constexpr int kRqThreads = 256;
+
+struct RqArgs {
+  const float* z; int64_t n; int n_levels; int n_levels_run; int resid_level;
+  const float* cb[LCREC_MAX_LEVELS]; int k[LCREC_MAX_LEVELS];
+  int64_t* codes; float* xq; float* resid_last; double* sq_err;
+};
+
+__device__ __forceinline__ double block_sum_double(double v, double* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = lane < (blockDim.x >> 5) ? scratch[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+// smem layout: for each staged level: codebook (k*D floats) then norms (k floats)
+template <int D>
+__global__ void __launch_bounds__(kRqThreads, 1) rq_quantize_smem_kernel(const RqArgs a) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ double red[kRqThreads / 32];
+  float* cbs[LCREC_MAX_LEVELS];
+  float* nrm[LCREC_MAX_LEVELS];
+  {
+    float* p = smem_f;
+    for (int l = 0; l < a.n_levels_run; ++l) { cbs[l] = p; p += (size_t)a.k[l] * D; nrm[l] = p; p += (a.k[l] + 3) & ~3; }
+  }
+  for (int l = 0; l < a.n_levels_run; ++l) {
+    const float4* src = reinterpret_cast<const float4*>(a.cb[l]);
+    float4* dst = reinterpret_cast<float4*>(cbs[l]);
+    for (int i = threadIdx.x; i < a.k[l] * D / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int l = 0; l < a.n_levels_run; ++l)
+    for (int c = threadIdx.x; c < a.k[l]; c += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(cbs[l][c * D + d], cbs[l][c * D + d], s);
+      nrm[l][c] = s;
+    }
+  __syncthreads();
+
+  double err[LCREC_MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < LCREC_MAX_LEVELS; ++l) err[l] = 0.0;
+
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < a.n;
+       item += (int64_t)gridDim.x * blockDim.x) {
+    float r[D], xq[D];
+    const float4* zp = reinterpret_cast<const float4*>(a.z + item * D);
+#pragma unroll
+    for (int d = 0; d < D / 4; ++d) {
+      const float4 t = __ldg(zp + d);
+      r[4 * d] = t.x; r[4 * d + 1] = t.y; r[4 * d + 2] = t.z; r[4 * d + 3] = t.w;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) xq[d] = 0.f;
+#pragma unroll 1
+    for (int l = 0; l < a.n_levels_run; ++l) {
+      if (a.resid_last != nullptr && l == a.resid_level) {
+        float4* rp = reinterpret_cast<float4*>(a.resid_last + item * D);
+#pragma unroll
+        for (int d = 0; d < D / 4; ++d) rp[d] = make_float4(r[4 * d], r[4 * d + 1], r[4 * d + 2], r[4 * d + 3]);
+      }
+      float xx = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) xx = fmaf(r[d], r[d], xx);
+      const float* cb = cbs[l];
+      const float* nr = nrm[l];
+      float best = INFINITY;
+      int best_k = 0;
+      const int kl = a.k[l];
+#pragma unroll 2
+      for (int c = 0; c < kl; ++c) {
+        const float4* cp = reinterpret_cast<const float4*>(cb + c * D);
+        float dot0 = 0.f, dot1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < D / 4; d += 2) {
+          const float4 u = cp[d];
+          dot0 = fmaf(r[4 * d], u.x, dot0); dot0 = fmaf(r[4 * d + 1], u.y, dot0);
+          dot0 = fmaf(r[4 * d + 2], u.z, dot0); dot0 = fmaf(r[4 * d + 3], u.w, dot0);
+          if (d + 1 < D / 4) {
+            const float4 w = cp[d + 1];
+            dot1 = fmaf(r[4 * d + 4], w.x, dot1); dot1 = fmaf(r[4 * d + 5], w.y, dot1);
+            dot1 = fmaf(r[4 * d + 6], w.z, dot1); dot1 = fmaf(r[4 * d + 7], w.w, dot1);
+          }
+        }
+        const float dist = (xx + nr[c]) - 2.f * (dot0 + dot1);
+        if (dist < best) { best = dist; best_k = c; }
+      }
+      if (a.codes) a.codes[item * a.n_levels + l] = best_k;
+      const float* q = cb + best_k * D;
+      double e = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float t = q[d] - r[d];
+        e += (double)(t * t);
+        const float xres = r[d] + t;
+        r[d] = r[d] - xres;
+        xq[d] += xres;
+      }
+      err[l] += e;
+    }
+    if (a.resid_last != nullptr && a.resid_level >= a.n_levels_run) {
+      float4* rp = reinterpret_cast<float4*>(a.resid_last + item * D);
+#pragma unroll
+      for (int d = 0; d < D / 4; ++d) rp[d] = make_float4(r[4 * d], r[4 * d + 1], r[4 * d + 2], r[4 * d + 3]);
+    }
+    if (a.xq) {
+      float4* xp = reinterpret_cast<float4*>(a.xq + item * D);
+#pragma unroll
+      for (int d = 0; d < D / 4; ++d) xp[d] = make_float4(xq[4 * d], xq[4 * d + 1], xq[4 * d + 2], xq[4 * d + 3]);
+    }
+  }
+  if (a.sq_err) {
+    for (int l = 0; l < a.n_levels_run; ++l) {
+      const double t = block_sum_double(err[l], red);
+      if (threadIdx.x == 0) atomicAdd(a.sq_err + l, t);
+    }
+  }
+}
+
+// Generic path: any e_dim / codebook size, codebooks read from global memory (L2).  One warp per
+// item; lanes stride over the codes; residual kept in shared memory.  Correct for every shape the
+// reference accepts; the large-codebook configuration (8192 x 256) is served by this kernel until
+// the tensor-core distance path lands.
+__global__ void __launch_bounds__(256) rq_quantize_generic_kernel(const RqArgs a, const int D,
+                                                                 const float* __restrict__ norms_all) {
+  extern __shared__ float sm[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* r = sm + (size_t)warp * 2 * D;
+  float* xq = r + D;
+  double err[LCREC_MAX_LEVELS];
+  for (int l = 0; l < LCREC_MAX_LEVELS; ++l) err[l] = 0.0;
+  for (int64_t item = blockIdx.x * (int64_t)warps + warp; item < a.n; item += (int64_t)gridDim.x * warps) {
+    for (int d = lane; d < D; d += 32) { r[d] = a.z[item * D + d]; xq[d] = 0.f; }
+    __syncwarp();
+    int norm_off = 0;
+    for (int l = 0; l < a.n_levels_run; ++l) {
+      if (a.resid_last != nullptr && l == a.resid_level)
+        for (int d = lane; d < D; d += 32) a.resid_last[item * D + d] = r[d];
+      float xx = 0.f;
+      for (int d = 0; d < D; ++d) xx = fmaf(r[d], r[d], xx);
+      float best = INFINITY; int best_k = 0x7fffffff;
+      const float* cb = a.cb[l];
+      for (int c = lane; c < a.k[l]; c += 32) {
+        const float* cp = cb + (size_t)c * D;
+        float dot = 0.f;
+        for (int d = 0; d < D; ++d) dot = fmaf(r[d], __ldg(cp + d), dot);
+        const float dist = (xx + norms_all[norm_off + c]) - 2.f * dot;
+        if (dist < best) { best = dist; best_k = c; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+      }
+      if (best_k == 0x7fffffff) best_k = 0;   // all-NaN row
+      if (lane == 0 && a.codes) a.codes[item * a.n_levels + l] = best_k;
+      const float* q = cb + (size_t)best_k * D;
+      double e = 0.0;
+      for (int d = lane; d < D; d += 32) {
+        const float t = __ldg(q + d) - r[d];
+        e += (double)(t * t);
+        const float xres = r[d] + t;
+        r[d] = r[d] - xres;
+        xq[d] += xres;
+      }
+      err[l] += e;
+      norm_off += a.k[l];
+      __syncwarp();
+    }
+    if (a.resid_last != nullptr && a.resid_level >= a.n_levels_run)
+      for (int d = lane; d < D; d += 32) a.resid_last[item * D + d] = r[d];
+    if (a.xq) for (int d = lane; d < D; d += 32) a.xq[item * D + d] = xq[d];
+    __syncwarp();
+  }
+  if (a.sq_err) {
+    __shared__ double red[8];
+    for (int l = 0; l < a.n_levels_run; ++l) {
+      const double t = block_sum_double(err[l], red);
+      if (threadIdx.x == 0) atomicAdd(a.sq_err + l, t);
+    }
+  }
+}
+
+__global__ void code_norms_kernel(const float* __restrict__ cb, int k, int D, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s = fmaf(cb[(size_t)c * D + d], cb[(size_t)c * D + d], s);
+  out[c] = s;
+}
+
+// d[i][k] = (|r_i|^2 + |c_k|^2) - 2 r_i.c_k   (vq.py:71-73); block = 256 threads over codes, rows by blockIdx
+__global__ void vq_distances_kernel(const float* __restrict__ r, int64_t n, int D, const float* __restrict__ cb,
+                                    int k, float* __restrict__ out) {
+  extern __shared__ float row[];
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) row[d] = r[i * D + d];
+    __syncthreads();
+    float xx = 0.f;
+    for (int d = 0; d < D; ++d) xx = fmaf(row[d], row[d], xx);
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+      const float* cp = cb + (size_t)c * D;
+      float cc = 0.f, dot = 0.f;
+      for (int d = 0; d < D; ++d) { const float v = __ldg(cp + d); cc = fmaf(v, v, cc); dot = fmaf(row[d], v, dot); }
+      out[i * k + c] = (xx + cc) - 2.f * dot;
+    }
+    __syncthreads();
+  }
+}
+
+template <int D>
+static int launch_rq_smem(const RqArgs& a, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) { LC_CUDA(cudaFuncSetAttribute(rq_quantize_smem_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  const int64_t blocks = std::min<int64_t>(ceil_div(a.n, kRqThreads), (int64_t)num_sms());
+  rq_quantize_smem_kernel<D><<<(unsigned)blocks, kRqThreads, smem, st>>>(a);
+  LC_LAUNCH_CHECK("rq_quantize_smem_kernel");
+  return LCREC_OK;
+}
+
+}  // namespace lcrec
+
+using namespace lcrec;
+
+extern "C" int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_levels, const float* const* codebooks,
+                                 const int32_t* n_codes, int n_levels_run, int resid_level, int64_t* codes,
+                                 float* xq, float* resid_last, double* sq_err, void* stream) {
+  LC_ARG(n >= 0 && e_dim > 0 && n_levels >= 1 && n_levels <= LCREC_MAX_LEVELS && codebooks && n_codes);
+  LC_ARG(n_levels_run >= 0 && n_levels_run <= n_levels);
+  LC_TRY(lcrec_device_check());
+  if (n == 0) return LCREC_OK;
+  LC_ARG(z != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  RqArgs a{};
+  a.z = z; a.n = n; a.n_levels = n_levels; a.n_levels_run = n_levels_run; a.resid_level = resid_level;
+  a.codes = codes; a.xq = xq; a.resid_last = resid_last; a.sq_err = sq_err;
+  size_t smem = 0; int64_t total_codes = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    LC_ARG(codebooks[l] != nullptr && n_codes[l] > 0);
+    a.cb[l] = codebooks[l]; a.k[l] = n_codes[l];
+    if (l < n_levels_run) { smem += sizeof(float) * ((size_t)n_codes[l] * e_dim + ((n_codes[l] + 3) & ~3)); total_codes += n_codes[l]; }
+  }
+  const bool aligned = (reinterpret_cast<uintptr_t>(z) & 15) == 0 && (!xq || (reinterpret_cast<uintptr_t>(xq) & 15) == 0) &&
+                       (!resid_last || (reinterpret_cast<uintptr_t>(resid_last) & 15) == 0);
+  bool cb_aligned = true;
+  for (int l = 0; l < n_levels_run; ++l) cb_aligned = cb_aligned && (reinterpret_cast<uintptr_t>(codebooks[l]) & 15) == 0;
+  if (smem <= 200 * 1024 && aligned && cb_aligned && n_levels_run > 0) {
+    if (e_dim == 32) return launch_rq_smem<32>(a, smem, st);
+    if (e_dim == 16) return launch_rq_smem<16>(a, smem, st);
+    if (e_dim == 64) return launch_rq_smem<64>(a, smem, st);
+  }
+  // generic path
+  float* norms = nullptr;
+  LC_CUDA(cudaMallocAsync(&norms, sizeof(float) * std::max<int64_t>(total_codes, 1), st));
+  int off = 0;
+  for (int l = 0; l < n_levels_run; ++l) {
+    code_norms_kernel<<<(unsigned)ceil_div(n_codes[l], 256), 256, 0, st>>>(codebooks[l], n_codes[l], e_dim, norms + off);
+    LC_LAUNCH_CHECK("code_norms_kernel");
+    off += n_codes[l];
+  }
+  const int warps = 8;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, warps), (int64_t)num_sms() * 8);
+  rq_quantize_generic_kernel<<<(unsigned)blocks, warps * 32, sizeof(float) * warps * 2 * e_dim, st>>>(a, e_dim, norms);
+  LC_LAUNCH_CHECK("rq_quantize_generic_kernel");
+  LC_CUDA(cudaFreeAsync(norms, st));
+  return LCREC_OK;
+}
+
+extern "C" int lcrec_vq_distances(const float* r, int64_t n, int e_dim, const float* codebook, int n_codes,
+                                  float* d, void* stream) {
+  LC_ARG(n >= 0 && e_dim > 0 && n_codes > 0 && codebook);
+  LC_TRY(lcrec_device_check());
+  if (n == 0) return LCREC_OK;
+  LC_ARG(r && d);
+  const int64_t blocks = std::min<int64_t>(n, (int64_t)num_sms() * 8);
+  vq_distances_kernel<<<(unsigned)blocks, 256, sizeof(float) * e_dim, (cudaStream_t)stream>>>(r, n, e_dim, codebook, n_codes, d);
+  LC_LAUNCH_CHECK("vq_distances_kernel");
+  return LCREC_OK;
+}

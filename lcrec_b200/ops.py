@@ -1,0 +1,337 @@
+"""Tensor-level wrappers over the C ABI.  torch provides device memory and streams only; every
+computation below happens inside liblcrec_b200.so (hand-written sm_100a kernels)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("lcrec_b200 operators run on a CUDA (sm_100a) device only; there is no CPU "
+                               f"fallback (got a tensor on {t.device})")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def launch_count() -> int:
+    return int(_lib.load().lcrec_launch_count())
+
+
+# --------------------------------------------------------------------------- MLP
+class MlpHandle:
+    """Prepared (3xTF32-split) weights of one MLPLayers stack."""
+
+    def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                 relu_last: bool = False):
+        _need_cuda(*weights)
+        self.lib = _lib.load()
+        self.device = weights[0].device
+        self.dims = [int(weights[0].shape[1])] + [int(w.shape[0]) for w in weights]
+        self.n_layers = len(weights)
+        self.handle = C.c_void_p()
+        ws, bs = self._pack(weights, biases)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lcrec_mlp_create(self.n_layers, _lib.i32_array(self.dims), ws, bs, int(relu_last),
+                                                 _stream(weights[0]), C.byref(self.handle)))
+        self._workspace: Optional[torch.Tensor] = None
+
+    def _pack(self, weights, biases):
+        self._keep = [_f32c(w) for w in weights]
+        self._keepb = [None if b is None else _f32c(b) for b in biases]
+        for w, (fi, fo) in zip(self._keep, zip(self.dims[:-1], self.dims[1:])):
+            assert tuple(w.shape) == (fo, fi)
+        return (_lib.ptr_array([w.data_ptr() for w in self._keep]),
+                _lib.ptr_array([0 if b is None else b.data_ptr() for b in self._keepb]))
+
+    def update(self, weights, biases) -> None:
+        ws, bs = self._pack(weights, biases)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lcrec_mlp_update(self.handle, ws, bs, _stream(self._keep[0])))
+
+    def set_acc_chunk(self, k_elems: int) -> None:
+        _lib.check(self.lib.lcrec_mlp_set_acc_chunk(self.handle, int(k_elems)))
+
+    def set_variant(self, v: int) -> None:
+        _lib.check(self.lib.lcrec_mlp_set_variant(self.handle, int(v)))
+
+    def forward(self, x: torch.Tensor, want_acts: bool = False):
+        _need_cuda(x)
+        x2 = _f32c(x.reshape(-1, self.dims[0]))
+        n = x2.shape[0]
+        y = torch.empty((n, self.dims[-1]), dtype=torch.float32, device=x2.device)
+        need = int(self.lib.lcrec_mlp_workspace_bytes(self.handle, n))
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != x2.device:
+            self._workspace = _ws(need, x2.device)
+        acts = None
+        acts_arr = None
+        if want_acts:
+            acts = [torch.empty((n, d), dtype=torch.float32, device=x2.device) for d in self.dims[1:-1]] + [y]
+            acts_arr = _lib.ptr_array([a.data_ptr() for a in acts])
+        with torch.cuda.device(x2.device):
+            _lib.check(self.lib.lcrec_mlp_forward(self.handle, _p(x2), n, _p(y), acts_arr, _p(self._workspace),
+                                                  self._workspace.numel(), _stream(x2)))
+        y = y.reshape(*x.shape[:-1], self.dims[-1])
+        return (y, acts) if want_acts else y
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.lcrec_mlp_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+def linear_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool,
+                   acc_chunk: int = 0, variant: int = 0) -> torch.Tensor:
+    """relu?(x @ w.T + b) with the 3xTF32 tcgen05 kernel (nn.Linear, layers.py:23)."""
+    _need_cuda(x, w)
+    lib = _lib.load()
+    x2, w2 = _f32c(x.reshape(-1, w.shape[1])), _f32c(w)
+    b2 = None if b is None else _f32c(b)
+    n, k, m = x2.shape[0], w2.shape[1], w2.shape[0]
+    y = torch.empty((n, m), dtype=torch.float32, device=x2.device)
+    ws = _ws(lib.lcrec_linear_workspace_bytes(n, k, m), x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.lcrec_linear_forward(_p(x2), n, k, _p(w2), _p(b2), m, int(relu), _p(y), int(acc_chunk),
+                                            int(variant), _p(ws), ws.numel(), _stream(x2)))
+    return y.reshape(*x.shape[:-1], m)
+
+
+# --------------------------------------------------------------------------- RQ
+def rq_quantize(z: torch.Tensor, codebooks: Sequence[torch.Tensor], n_levels_run: Optional[int] = None,
+                resid_level: int = -1, want_codes: bool = True, want_xq: bool = False,
+                want_sq_err: bool = False):
+    """Fused argmin residual quantisation over ``codebooks[:n_levels_run]`` (rq.py:39-56).
+
+    Returns dict with codes (n, L_run) int64, xq (n, D), resid (residual entering ``resid_level``;
+    ``resid_level == n_levels_run`` gives the residual left after the last level run), sq_err (L_run) fp64.
+    """
+    _need_cuda(z, *codebooks)
+    lib = _lib.load()
+    d = int(codebooks[0].shape[1])
+    z2 = _f32c(z.reshape(-1, d))
+    n = z2.shape[0]
+    cbs = [_f32c(c) for c in codebooks]
+    run = len(cbs) if n_levels_run is None else int(n_levels_run)
+    cbs = cbs[:max(run, 1)]
+    L = len(cbs)
+    dev = z2.device
+    codes = torch.empty((n, L), dtype=torch.int64, device=dev) if want_codes else None
+    xq = torch.empty((n, d), dtype=torch.float32, device=dev) if want_xq else None
+    resid = torch.empty((n, d), dtype=torch.float32, device=dev) if resid_level >= 0 else None
+    err = torch.zeros((L,), dtype=torch.float64, device=dev) if want_sq_err else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.lcrec_rq_quantize(_p(z2), n, d, L, _lib.ptr_array([c.data_ptr() for c in cbs]),
+                                         _lib.i32_array([c.shape[0] for c in cbs]), run, int(resid_level), _p(codes),
+                                         _p(xq), _p(resid), _p(err), _stream(z2)))
+    if codes is not None and run < L:
+        codes = codes[:, :run]
+    return {"codes": codes, "xq": xq, "resid": resid, "sq_err": err}
+
+
+def vq_distances(r: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    """(n, K) fp32 distances of vq.py:71-73."""
+    _need_cuda(r, codebook)
+    lib = _lib.load()
+    cb = _f32c(codebook)
+    r2 = _f32c(r.reshape(-1, cb.shape[1]))
+    out = torch.empty((r2.shape[0], cb.shape[0]), dtype=torch.float32, device=r2.device)
+    with torch.cuda.device(r2.device):
+        _lib.check(lib.lcrec_vq_distances(_p(r2), r2.shape[0], cb.shape[1], _p(cb), cb.shape[0], _p(out), _stream(r2)))
+    return out
+
+
+# --------------------------------------------------------------------------- Sinkhorn
+def center_distances(d: torch.Tensor) -> torch.Tensor:
+    """center_distance_for_constraint (vq.py:51-61) followed by .double() (vq.py:78)."""
+    _need_cuda(d)
+    lib = _lib.load()
+    d2 = _f32c(d)
+    out = torch.empty(d2.shape, dtype=torch.float64, device=d2.device)
+    status = torch.zeros(1, dtype=torch.int32, device=d2.device)
+    ws = _ws(16384, d2.device)
+    with torch.cuda.device(d2.device):
+        _lib.check(lib.lcrec_center_distances(_p(d2), d2.shape[0], d2.shape[1], _p(out), _p(status), _p(ws),
+                                              ws.numel(), _stream(d2)))
+    if int(status.item()) != 0:
+        raise AssertionError("amplitude > 0")      # vq.py:59
+    return out
+
+
+def sinkhorn_dense(distances: torch.Tensor, epsilon: float, iters: int, want_argmax: bool = False):
+    """sinkhorn_algorithm (layers.py:85-108) on a CUDA fp64 matrix; optional fused argmax (vq.py:83)."""
+    _need_cuda(distances)
+    lib = _lib.load()
+    d = distances.detach().to(torch.float64).contiguous()
+    b, k = d.shape
+    q = torch.empty_like(d)
+    arg = torch.empty((b,), dtype=torch.int64, device=d.device) if want_argmax else None
+    flags = torch.zeros(1, dtype=torch.int32, device=d.device)
+    ws = _ws(lib.lcrec_sinkhorn_workspace_bytes(b, k), d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(lib.lcrec_sinkhorn_dense(_p(d), b, k, float(epsilon), int(iters), _p(q), _p(arg), _p(flags), _p(ws),
+                                            ws.numel(), _stream(d)))
+    return (q, arg, flags) if want_argmax else q
+
+
+def collisions(codes: torch.Tensor, n_codes: Sequence[int]):
+    """Sort/unique over packed code tuples -> CSR collision groups + counts (generate_indices.py:18-42)."""
+    _need_cuda(codes)
+    lib = _lib.load()
+    c = codes.detach().to(torch.int64).contiguous()
+    n, L = c.shape
+    dev = c.device
+    offsets = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    members = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    counts = torch.zeros((4,), dtype=torch.int64, device=dev)
+    ws = _ws(lib.lcrec_collisions_workspace_bytes(n), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lcrec_collisions(_p(c), n, L, _lib.i32_array(n_codes), _p(offsets), _p(members), _p(counts),
+                                        _p(ws), ws.numel(), _stream(c)))
+    n_unique, n_groups, n_rows, max_mult = [int(v) for v in counts.tolist()]
+    return {"offsets": offsets[: n_groups + 1], "members": members[:n_rows], "n_unique": n_unique,
+            "n_groups": n_groups, "n_rows": n_rows, "max_multiplicity": max_mult, "counts_dev": counts}
+
+
+def sort_codes(codes: torch.Tensor, n_codes: Sequence[int]):
+    _need_cuda(codes)
+    lib = _lib.load()
+    c = codes.detach().to(torch.int64).contiguous()
+    n, L = c.shape
+    keys = torch.empty((n,), dtype=torch.int64, device=c.device)
+    items = torch.empty((n,), dtype=torch.int32, device=c.device)
+    ws = _ws(lib.lcrec_collisions_workspace_bytes(n), c.device)
+    with torch.cuda.device(c.device):
+        _lib.check(lib.lcrec_sort_codes(_p(c), n, L, _lib.i32_array(n_codes), _p(keys), _p(items), _p(ws), ws.numel(),
+                                        _stream(c)))
+    return keys, items
+
+
+def sinkhorn_groups(resid: torch.Tensor, codebook: torch.Tensor, offsets: torch.Tensor, members: torch.Tensor,
+                    n_groups_dev: torch.Tensor, max_groups: int, max_rows: int, epsilon: float, iters: int,
+                    codes: torch.Tensor, level: int) -> int:
+    """Per-group Sinkhorn re-assignment of ``codes[:, level]`` in place; returns the flag word."""
+    _need_cuda(resid, codebook, offsets, members, codes)
+    lib = _lib.load()
+    assert codes.dtype == torch.int64 and codes.is_contiguous()
+    r, cb = _f32c(resid), _f32c(codebook)
+    flags = torch.zeros(2, dtype=torch.int32, device=r.device)
+    ws = _ws(lib.lcrec_sinkhorn_groups_workspace_bytes(max_rows, cb.shape[0]), r.device)
+    with torch.cuda.device(r.device):
+        _lib.check(lib.lcrec_sinkhorn_groups(_p(r), cb.shape[1], _p(cb), cb.shape[0], _p(offsets), _p(members),
+                                             _p(n_groups_dev), int(max_groups), int(max_rows), float(epsilon), int(iters),
+                                             _p(codes), codes.shape[1], int(level), _p(flags), _p(ws), ws.numel(),
+                                             _stream(r)))
+    return int(flags[0].item())
+
+
+# --------------------------------------------------------------------------- whole generation
+class Indexer:
+    """generate_indices.py:85-128 on the device (PASS 0 + collision rounds)."""
+
+    def __init__(self, encoder: MlpHandle, codebooks: Sequence[torch.Tensor], last_epsilon: float, sk_iters: int,
+                 max_items: int, chunk_rows: int = 131072):
+        self.lib = _lib.load()
+        self.encoder = encoder
+        self.cbs = [_f32c(c) for c in codebooks]
+        _need_cuda(*self.cbs)
+        self.L = len(self.cbs)
+        self.D = int(self.cbs[0].shape[1])
+        self.device = self.cbs[0].device
+        self.max_items = int(max_items)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lcrec_indexer_create(encoder.handle, self.D, self.L,
+                                                     _lib.ptr_array([c.data_ptr() for c in self.cbs]),
+                                                     _lib.i32_array([c.shape[0] for c in self.cbs]), float(last_epsilon),
+                                                     int(sk_iters), self.max_items, int(chunk_rows), C.byref(self.handle)))
+
+    def _stats(self, raw) -> dict:
+        keys = ["rounds", "n_unique", "groups_round1", "rows_round1", "sinkhorn_rows", "max_multiplicity", "nan_flag"]
+        return {k: int(raw[i]) for i, k in enumerate(keys)}
+
+    def run_device(self, x: torch.Tensor, max_rounds: int = 20) -> Tuple[torch.Tensor, dict]:
+        _need_cuda(x)
+        x2 = _f32c(x)
+        n = x2.shape[0]
+        codes = torch.empty((n, self.L), dtype=torch.int64, device=x2.device)
+        stats = (C.c_int64 * 8)()
+        with torch.cuda.device(x2.device):
+            _lib.check(self.lib.lcrec_indexer_run_device(self.handle, _p(x2), n, int(max_rounds), _p(codes), stats,
+                                                         _stream(x2)))
+        return codes, self._stats(stats)
+
+    def run_host(self, x_host, codes_host=None, max_rounds: int = 20):
+        """x_host: CPU float32 tensor / ndarray (n, in_dim) (pinned or pageable); returns CPU int64 codes."""
+        xt = torch.as_tensor(x_host)
+        assert not xt.is_cuda and xt.dtype == torch.float32 and xt.is_contiguous()
+        n = xt.shape[0]
+        out = torch.empty((n, self.L), dtype=torch.int64) if codes_host is None else codes_host
+        stats = (C.c_int64 * 8)()
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.lcrec_indexer_run_host(self.handle, C.c_void_p(xt.data_ptr()), n, int(max_rounds),
+                                                       C.c_void_p(out.data_ptr()), stats, st))
+        return out, self._stats(stats)
+
+    def pass0(self, x: torch.Tensor, row_offset: int = 0) -> None:
+        x2 = _f32c(x)
+        with torch.cuda.device(x2.device):
+            _lib.check(self.lib.lcrec_indexer_pass0(self.handle, _p(x2), x2.shape[0], int(row_offset), _stream(x2)))
+
+    def round(self, n: int) -> dict:
+        counts = (C.c_int64 * 4)()
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.lcrec_indexer_round(self.handle, int(n), counts, st))
+        return {"n_unique": int(counts[0]), "n_groups": int(counts[1]), "n_rows": int(counts[2]),
+                "max_multiplicity": int(counts[3])}
+
+    def _view(self, ptr: int, shape, dtype) -> torch.Tensor:
+        import numpy as np  # local: only for the dtype size
+        n = 1
+        for s in shape:
+            n *= s
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        # wrap borrowed device memory without copying (torch has no public from-pointer; use __cuda_array_interface__)
+        class _Holder:
+            pass
+        h = _Holder()
+        typestr = {torch.int64: "<i8", torch.float32: "<f4"}[dtype]
+        h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+        return torch.as_tensor(h, device=self.device)
+
+    def codes_view(self, n: int) -> torch.Tensor:
+        return self._view(self.lib.lcrec_indexer_codes(self.handle), (n, self.L), torch.int64)
+
+    def resid_view(self, n: int) -> torch.Tensor:
+        return self._view(self.lib.lcrec_indexer_resid(self.handle), (n, self.D), torch.float32)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.lcrec_indexer_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
