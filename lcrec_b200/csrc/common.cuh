@@ -19,6 +19,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess) {                                                                 \
       lcrec::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (void)cudaGetLastError();                                                              \
       return LCREC_ERR_CUDA;                                                                 \
     }                                                                                        \
   } while (0)

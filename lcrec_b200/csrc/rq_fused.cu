@@ -236,7 +236,7 @@ __global__ void vq_distances_kernel(const float* __restrict__ r, int64_t n, int 
 template <int D>
 static int launch_rq_smem(const RqArgs& a, size_t smem, cudaStream_t st) {
   static bool attr = false;
-  if (!attr) { LC_CUDA(cudaFuncSetAttribute(rq_quantize_smem_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  if (!attr) { LC_CUDA(cudaFuncSetAttribute(rq_quantize_smem_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
   const int64_t blocks = std::min<int64_t>(ceil_div(a.n, kRqThreads), (int64_t)num_sms());
   rq_quantize_smem_kernel<D><<<(unsigned)blocks, kRqThreads, smem, st>>>(a);
   LC_LAUNCH_CHECK("rq_quantize_smem_kernel");

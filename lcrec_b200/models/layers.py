@@ -1,0 +1,193 @@
+"""MLP stack, k-means initialiser and Sinkhorn entry point with the reference's import surface.
+
+Mirrors ``index/models/layers.py`` of the reference (``MLPLayers`` :7-43, ``activation_layer``
+:45-67, ``kmeans`` :69-82, ``sinkhorn_algorithm`` :85-108): same constructor arguments, same
+sub-module layout (so ``state_dict`` keys ``mlp_layers.{i}.weight`` ... are interchangeable with
+reference checkpoints), but the arithmetic runs in liblcrec_b200.so:
+
+* inference (no autograd): the whole stack is one ``MlpHandle`` - tcgen05 3xTF32 GEMMs with fused
+  bias + ReLU, activations handed from layer to layer already split; eval-mode BatchNorm is folded
+  into the weights;
+* training: each ``nn.Linear`` (+ReLU when nothing sits between them) goes through the same GEMM
+  kernel inside an autograd Function; BatchNorm / Dropout / non-ReLU activations stay torch modules.
+
+CUDA only - a CPU tensor raises (no fallback).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def activation_layer(activation_name="relu", emb_dim=None):
+    """Activation factory, same accepted names / errors as reference layers.py:45-67."""
+    if activation_name is None:
+        return None
+    if isinstance(activation_name, str):
+        table = {"sigmoid": nn.Sigmoid, "tanh": nn.Tanh, "relu": nn.ReLU, "leakyrelu": nn.LeakyReLU, "none": None}
+        key = activation_name.lower()
+        ctor = table.get(key)            # unknown strings give None, as in the reference
+        return ctor() if ctor is not None else None
+    if isinstance(activation_name, type) and issubclass(activation_name, nn.Module):
+        return activation_name()
+    raise NotImplementedError("activation function {} is not implemented".format(activation_name))
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = relu?(x W^T + b): forward on the tcgen05 kernel; backward GEMMs are plain library
+    matmuls (fp32, TF32 off) - see DESIGN.md "training path"."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, fuse_relu: bool):
+        y = ops.linear_forward(x, weight, bias, fuse_relu)
+        ctx.fuse_relu = fuse_relu
+        ctx.save_for_backward(x, weight, y if fuse_relu else None)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        if ctx.fuse_relu:
+            gy = gy * (y > 0).to(gy.dtype)
+        gy2 = gy.reshape(-1, gy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (gy2 @ weight).reshape(x.shape)
+        if ctx.needs_input_grad[1]:
+            gw = gy2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy2.sum(0)
+        return gx, gw, gb, None
+
+
+class MLPLayers(nn.Module):
+    def __init__(self, layers, dropout=0.0, activation="relu", bn=False):
+        super().__init__()
+        self.layers = layers
+        self.dropout = dropout
+        self.activation = activation
+        self.use_bn = bn
+
+        mods: List[nn.Module] = []
+        n_lin = len(layers) - 1
+        for i in range(n_lin):
+            mods.append(nn.Dropout(p=dropout))
+            mods.append(nn.Linear(layers[i], layers[i + 1]))
+            if i != n_lin - 1:
+                if bn:
+                    mods.append(nn.BatchNorm1d(num_features=layers[i + 1]))
+                act = activation_layer(activation, layers[i + 1])
+                if act is not None:
+                    mods.append(act)
+        self.mlp_layers = nn.Sequential(*mods)
+        self.apply(self.init_weights)
+        self._handle: Optional[ops.MlpHandle] = None
+        self._handle_key = None
+
+    def init_weights(self, module):
+        if isinstance(module, nn.Linear):           # Xavier-normal W, zero b (reference layers.py:35-40)
+            nn.init.xavier_normal_(module.weight.data)
+            if module.bias is not None:
+                module.bias.data.fill_(0.0)
+
+    # ------------------------------------------------------------------ structure helpers
+    def _blocks(self):
+        """[(dropout, linear, bn|None, act|None)] in order."""
+        blocks, cur = [], None
+        for m in self.mlp_layers:
+            if isinstance(m, nn.Dropout):
+                if cur is not None:
+                    blocks.append(cur)
+                cur = [m, None, None, None]
+            elif isinstance(m, nn.Linear):
+                cur[1] = m
+            elif isinstance(m, nn.BatchNorm1d):
+                cur[2] = m
+            else:
+                cur[3] = m
+        blocks.append(cur)
+        return blocks
+
+    def _fused_ok(self) -> bool:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return False
+        blocks = self._blocks()
+        for i, (dp, lin, bn, act) in enumerate(blocks):
+            last = i == len(blocks) - 1
+            if self.training and (dp.p > 0 or bn is not None):
+                return False
+            if not last and not isinstance(act, nn.ReLU):
+                return False
+            if lin.out_features % 4 != 0 and last:
+                return False
+        return True
+
+    def _folded(self):
+        """(weights, biases) with eval-mode BatchNorm folded in (computed in fp64, rounded once)."""
+        ws, bs = [], []
+        for dp, lin, bn, act in self._blocks():
+            w = lin.weight.detach()
+            b = lin.bias.detach() if lin.bias is not None else torch.zeros(lin.out_features, device=w.device)
+            if bn is not None:
+                inv = 1.0 / torch.sqrt(bn.running_var.double() + bn.eps)
+                g = bn.weight.detach().double() if bn.affine else torch.ones_like(inv)
+                beta = bn.bias.detach().double() if bn.affine else torch.zeros_like(inv)
+                s = g * inv
+                w = (w.double() * s[:, None]).float()
+                b = ((b.double() - bn.running_mean.double()) * s + beta).float()
+            ws.append(w)
+            bs.append(b)
+        return ws, bs
+
+    def _get_handle(self) -> ops.MlpHandle:
+        key = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if self._handle is None or self._handle_key != key:
+            ws, bs = self._folded()
+            if self._handle is not None and self._handle.device == ws[0].device:
+                self._handle.update(ws, bs)
+            else:
+                self._handle = ops.MlpHandle(ws, bs, relu_last=False)
+            self._handle_key = key
+        return self._handle
+
+    def forward(self, input_feature):
+        if not input_feature.is_cuda:
+            raise RuntimeError("lcrec_b200.MLPLayers runs on CUDA only (no CPU fallback)")
+        if self._fused_ok():
+            return self._get_handle().forward(input_feature)
+        x = input_feature
+        blocks = self._blocks()
+        for i, (dp, lin, bn, act) in enumerate(blocks):
+            x = dp(x)
+            fuse = bn is None and isinstance(act, nn.ReLU)
+            x = _LinearFn.apply(x, lin.weight, lin.bias, fuse)
+            if bn is not None:
+                x = bn(x)
+            if act is not None and not fuse:
+                x = act(x)
+        return x
+
+
+def kmeans(samples, num_clusters, num_iters=10):
+    """Codebook initialisation (reference layers.py:69-82).  Delegated to scikit-learn exactly as
+    the reference does (k-means++ seeding from numpy's global RNG) so that initial codebooks are
+    reproducible against it; a device k-means is listed under 'next' in DESIGN.md."""
+    from sklearn.cluster import KMeans
+    x = samples.detach().cpu().numpy()
+    fit = KMeans(n_clusters=num_clusters, max_iter=num_iters).fit(x)
+    return torch.from_numpy(fit.cluster_centers_).to(samples.device)
+
+
+@torch.no_grad()
+def sinkhorn_algorithm(distances, epsilon, sinkhorn_iterations):
+    """Drop-in for reference layers.py:85-108 on a CUDA tensor: returns the transport plan Q with
+    the reference's literal normalisation order, computed by the fp64 cooperative kernel.  Inputs
+    that are not fp64 are promoted (fp32 overflows at eps=0.003) and the result cast back."""
+    q = ops.sinkhorn_dense(distances, float(epsilon), int(sinkhorn_iterations))
+    return q if distances.dtype == torch.float64 else q.to(distances.dtype)
