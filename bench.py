@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the LC-Rec item-indexing hot path on B200 (metric of BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the reference algorithm on host cores
+
+A step = one full pass of index generation (generate_indices.py:85-128: encoder -> 4-level residual
+quantisation -> up to 20 rounds of sort/unique + per-group Sinkhorn) over the whole synthetic item set.
+Workload (BASELINE.json configs[2], the largest that fits one GPU): 1 M items x 4096-d fp32 per GPU,
+encoder 4096-2048-1024-512-256-128-64-32, 4 x 256 codes, e_dim 32, eps_last 0.003, 50 Sinkhorn
+iterations; for N > 1 every rank holds its own 1 M items (weak scaling, BASELINE.json configs[3] shape)
+and the ranks resolve collisions over the union (code all-gather + per-round delta all-reduce, NCCL).
+Inputs (16.4 GB per GPU) are larger than the 126 MB L2, so no flush is needed between steps.
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIMS = [4096, 2048, 1024, 512, 256, 128, 64, 32]
+N_CODES = [256, 256, 256, 256]
+E_DIM = 32
+EPS_LAST = 0.003
+SK_ITERS = 50
+SEED_W = 77
+SEED_X = 2024
+HEAD_ITEMS = 8192          # numpy-generated head of the item stream, shared with the CPU arm
+BYTES_PER_ITEM = DIMS[0] * 4 + len(N_CODES) * 8                       # 16 416 B
+FLOP_PER_ITEM = 2 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:])) + len(N_CODES) * 2 * 256 * E_DIM   # 22 433 792
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------- workload (numpy, shared by both arms)
+def np_mlp(x, ws, bs):
+    h = x
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        h = h @ w.T + b
+        if i != len(ws) - 1:
+            h = np.maximum(h, 0)
+    return h.astype(np.float32)
+
+
+def make_model():
+    """Seeded encoder weights + data-driven codebooks (sample init + 4 Lloyd steps per level on the
+    latents of the stream head).  Pure numpy so that the CPU arm and the GPU arm hold identical parameters."""
+    from lcrec_b200.synth import seeded_weights, synth_items
+    ws, bs, _ = seeded_weights(DIMS, N_CODES, E_DIM, seed=SEED_W)
+    head = synth_items(HEAD_ITEMS, DIMS[0], n_parents=HEAD_ITEMS // 8, seed=SEED_X)
+    z = np_mlp(head, ws, bs)
+    rng = np.random.default_rng(5)
+    resid = z.copy()
+    cbs = []
+    for k in N_CODES:
+        cb = resid[rng.choice(resid.shape[0], k, replace=False)].copy()
+        for _ in range(4):
+            d = (resid ** 2).sum(1, keepdims=True) + (cb ** 2).sum(1)[None] - 2 * resid @ cb.T
+            a = d.argmin(1)
+            for c in range(k):
+                m = a == c
+                if m.any():
+                    cb[c] = resid[m].mean(0)
+        d = (resid ** 2).sum(1, keepdims=True) + (cb ** 2).sum(1)[None] - 2 * resid @ cb.T
+        resid = resid - cb[d.argmin(1)]
+        cbs.append(cb.astype(np.float32))
+    return ws, bs, cbs, head
+
+
+def make_items_device(n, head, device, rank):
+    """n items on the device: the numpy head first, the rest from the same generator family with the
+    torch device RNG (low-rank parents + 0.05 noise, ~8 near-duplicates per parent)."""
+    import torch
+    from lcrec_b200.synth import lowrank_map, RANK
+    x = torch.empty((n, DIMS[0]), dtype=torch.float32, device=device)
+    h = min(n, head.shape[0]) if rank == 0 else 0
+    if h:
+        x[:h] = torch.from_numpy(head[:h]).to(device)
+    g = torch.Generator(device=device).manual_seed(SEED_X + 1000 * rank)
+    gmap = torch.from_numpy(lowrank_map(DIMS[0])).to(device)
+    n_par = max((n - h) // 8, 1)
+    parents = torch.randn((n_par, RANK), device=device, generator=g)
+    for s in range(h, n, 65536):
+        m = min(65536, n - s)
+        pid = torch.randint(0, n_par, (m,), device=device, generator=g)
+        x[s:s + m] = parents[pid] @ gmap
+        x[s:s + m].add_(torch.randn((m, DIMS[0]), device=device, generator=g), alpha=0.05)
+    return x
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.path = tempfile.mktemp(prefix="lcrec_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample_run(ws, bs, cbs, head, n_sample):
+    """The reference algorithm (numpy restatement, literal per-group re-encoding like
+    generate_indices.py:116-119) on a bounded sample; returns (items/s, seconds, stats)."""
+    from oracle import lcrec_oracle as O
+    p = O.RqvaeParams(encoder=O.MlpParams(ws, bs), codebooks=cbs, sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST], sk_iters=SK_ITERS)
+    x = head[:n_sample]
+    t0 = time.perf_counter()
+    codes, trace = O.generate_indices(x, p, batch_size=64, max_rounds=20, reencode=True)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt, {"rounds": len(trace.rounds), "collision_rate_pass0": O.collision_rate(trace.codes_pass0),
+                               "collision_rate_final": O.collision_rate(codes)}
+
+
+def host_threads():
+    try:
+        import threadpoolctl
+        info = threadpoolctl.threadpool_info()
+        n = max([i.get("num_threads", 1) for i in info] or [1])
+        return int(n)
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ws, bs, cbs, head = make_model()
+    n_sample = a.cpu_sample
+    vals = []
+    for i in range(a.warmup + a.steps):
+        v, dt, st = cpu_sample_run(ws, bs, cbs, head, n_sample)
+        if i >= a.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    cores = host_threads()
+    sample = f"{n_sample} items of the same stream (numpy head), full generate_indices incl. per-group re-encoding, per step"
+    line = {"impl": "reference", "metric": "items indexed/sec (4-level RQ + Sinkhorn collision resolution)", "value": value,
+            "unit": "items/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a.gpus, a.items),
+            "cpu_baseline": {"value": value, "unit": "items/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "collision": st}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(gpus, items):
+    return {"workload": f"full index generation + collision resolution, {items} synthetic 4096-d items per GPU "
+                        f"(BASELINE.json configs[2]; x{gpus} GPUs = configs[3] shape)",
+            "items_per_gpu": items, "in_dim": DIMS[0], "encoder": DIMS, "levels": len(N_CODES), "codes_per_level": 256,
+            "e_dim": E_DIM, "sk_epsilon_last": EPS_LAST, "sk_iters": SK_ITERS, "max_rounds": 20,
+            "l2_policy": "inputs (16.4 GB/GPU) larger than L2, no flush", "parallelism": f"items sharded x{gpus}"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from lcrec_b200 import ops
+    from lcrec_b200.distributed import CudaBackend, ShardPlan, generate_codes_sharded
+    from lcrec_b200.models import RQVAE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pk = peaks()
+    ws, bs, cbs, head = make_model()
+    n_local = a.items
+    model = RQVAE(in_dim=DIMS[0], num_emb_list=N_CODES, e_dim=E_DIM, layers=DIMS[1:-1], sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST],
+                  sk_iters=SK_ITERS)
+    sd = model.state_dict()
+    lin = sorted([k for k in sd if k.startswith("encoder.mlp_layers.") and k.endswith(".weight")], key=lambda s: int(s.split(".")[2]))
+    for k, w, b in zip(lin, ws, bs):
+        sd[k] = torch.from_numpy(w); sd[k.replace(".weight", ".bias")] = torch.from_numpy(b)
+    for l, cb in enumerate(cbs):
+        sd[f"rq.vq_layers.{l}.embedding.weight"] = torch.from_numpy(cb)
+    model.load_state_dict(sd)
+    model = model.to(device).eval()
+    x = make_items_device(n_local, head, device, rank)
+    plan = ShardPlan(n_local * world, world)
+    backend = CudaBackend(model, n_local, a.chunk_rows)
+    ix = backend.indexer
+
+    def step():
+        if world == 1:
+            return ix.run_device(x, 20)
+        return generate_codes_sharded(backend, x, plan, rank, 20)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        codes, stats = step()
+    barrier()
+    ops.profile_enable(True)
+    ops.profile_collect()
+    launches0 = ops.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        codes, stats = step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = ops.launch_count() - launches0
+    prof = ops.profile_collect()
+    ops.profile_enable(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+    value = n_local * world / (ms_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (pinned input, H2D + D2H inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        n_e2e = min(n_local, a.e2e_items)
+        xh = torch.empty((n_e2e, DIMS[0]), dtype=torch.float32, pin_memory=True)
+        xh.copy_(x[:n_e2e])
+        out_h = torch.empty((n_e2e, len(N_CODES)), dtype=torch.int64, pin_memory=True)
+        ix.run_host(xh, out_h, 20)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        reps = max(1, min(a.steps, 3))
+        for _ in range(reps):
+            ix.run_host(xh, out_h, 20)
+        e1.record()
+        barrier()
+        ms_e = e0.elapsed_time(e1) / reps
+        te = torch.tensor([ms_e], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_e2e * world / (float(te.item()) * 1e-3), "unit": "items/s", "h2d_bytes_per_step": n_e2e * DIMS[0] * 4,
+               "d2h_bytes_per_step": n_e2e * len(N_CODES) * 8, "items_per_gpu": n_e2e,
+               "note": "lcrec_indexer_run_host: pinned host embeddings -> codes in host memory; each rank indexes its own items"}
+        del xh
+
+    if rank == 0:
+        # roofline of the dominant kernel: encoder layer 1 (4096 -> 2048), tcgen05 3xTF32
+        l1_ms, l1_calls = prof.get(1, (0.0, 0))
+        rows_per_launch = min(a.chunk_rows, n_local)
+        flops_launch = 2.0 * DIMS[0] * DIMS[1] * (n_local * a.steps / max(l1_calls, 1))
+        ach = flops_launch / (l1_ms / max(l1_calls, 1) * 1e-3) / 1e12 if l1_calls else None
+        stage_ms = {str(k): round(v[0] / a.steps, 4) for k, v in sorted(prof.items())}
+        roof = {"bound": "tensor", "kernel": "linear_tf32x3_kernel<256,16,4> (encoder layer 1, 4096->2048)",
+                "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["bf16_sustained"]) if ach else None,
+                "traffic": None, "peak_source": pk["source"] + ", bf16 dense sustained",
+                "note": "achieved = algorithmic fp32 GEMM FLOPs (2*M*4096*2048 per launch) / CUDA-event launch time; the kernel issues 3 TF32 "
+                        "MMAs per product (fp32-accurate split), i.e. tensor work = 3x achieved at half the bf16 rate: ceiling = peak/6",
+                "tensor_work_tflops": 3 * ach if ach else None, "frac_of_3xtf32_ceiling": (ach / (pk["bf16_sustained"] / 6)) if ach else None,
+                "launches": l1_calls, "avg_launch_ms": l1_ms / max(l1_calls, 1), "rows_per_launch": rows_per_launch,
+                "kernel_share_of_step": l1_ms / a.steps / ms_step,
+                "hbm_frac_end_to_end": value / world * BYTES_PER_ITEM / 1e9 / pk["hbm_gbs"], "stage_ms_per_step": stage_ms}
+        cpu = None
+        if world == 1 and not a.no_cpu:
+            v, dt, st = cpu_sample_run(ws, bs, cbs, head, a.cpu_sample)
+            cpu = {"value": v, "unit": "items/s", "cores": host_threads(), "kind": "port", "seconds": dt,
+                   "sample": f"{a.cpu_sample} items of the same stream, full generate_indices incl. per-group re-encoding (numpy/OpenBLAS)"}
+        line = {"metric": "items indexed/sec (4-level RQ + Sinkhorn collision resolution)", "value": value, "unit": "items/s",
+                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (low-rank parents + noise, random-init encoder, k-means-style codebooks)",
+                "config": workload_config(world, n_local), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "stats": stats,
+                "flop_per_item": FLOP_PER_ITEM, "bytes_per_item": BYTES_PER_ITEM,
+                "algorithmic_tflops_end_to_end": value * FLOP_PER_ITEM / 1e12}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--items", type=int, default=1_000_000, help="items per GPU")
+    ap.add_argument("--chunk-rows", dest="chunk_rows", type=int, default=131072)
+    ap.add_argument("--e2e-items", dest="e2e_items", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=2048)
+    ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 0)
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    return run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -111,6 +111,14 @@ int lcrec_sinkhorn_groups(const float* resid, int e_dim, const float* codebook, 
                           int64_t* codes, int n_levels, int level, int32_t* flags, void* ws,
                           int64_t ws_bytes, void* stream);
 
+/* Same, restricted to groups g with g % part_mod == part_rem: the multi-GPU split of one round
+ * (every rank sees the same CSR, resolves its share, last-level code deltas are all-reduced). */
+int lcrec_sinkhorn_groups_part(const float* resid, int e_dim, const float* codebook, int n_codes,
+                               const int64_t* offsets, const int64_t* members, const int64_t* n_groups_dev,
+                               int64_t max_groups, int64_t max_rows, double epsilon, int iters,
+                               int64_t* codes, int n_levels, int level, int part_mod, int part_rem,
+                               int32_t* flags, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- a12/a14: collision bookkeeping (generate_indices.py:18-42, trainer.py:141-150) -----
  * Packs (n, L) int64 codes into u64 keys, radix-sorts (key, item) and emits collision groups
  * in CSR form: groups ordered by key, members ascending (the reference orders groups by
@@ -148,6 +156,11 @@ int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t n, int64_t 
 int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* counts_host, void* stream);
 int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
 float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */
+/* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).
+ * Tags: 0 = 3xTF32 split of the input, 1+l = MLP layer l, 20 = fused RQ, 21 = sort/unique,
+ * 22 = per-group Sinkhorn.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */
+int lcrec_profile_enable(int on);
+int lcrec_profile_collect(double* ms, int64_t* calls);
 /* number of kernels this library has launched on the calling process so far */
 int64_t lcrec_launch_count(void);
 

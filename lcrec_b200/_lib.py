@@ -41,9 +41,13 @@ SIGNATURES = {
     "lcrec_sinkhorn_groups_workspace_bytes": (i64, [i64, C.c_int]),
     "lcrec_sinkhorn_groups": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, f64, C.c_int, vp, C.c_int,
                                         C.c_int, vp, vp, i64, vp]),
+    "lcrec_sinkhorn_groups_part": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, f64, C.c_int, vp, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, vp, vp, i64, vp]),
     "lcrec_collisions_workspace_bytes": (i64, [i64]),
     "lcrec_collisions": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, vp, i64, vp]),
     "lcrec_sort_codes": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, i64, vp]),
+    "lcrec_profile_enable": (C.c_int, [C.c_int]),
+    "lcrec_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64)]),
     "lcrec_indexer_create": (C.c_int, [vp, C.c_int, C.c_int, pp, C.POINTER(i32), f64, C.c_int, i64, i64, pp]),
     "lcrec_indexer_destroy": (C.c_int, [vp]),
     "lcrec_indexer_run_device": (C.c_int, [vp, vp, i64, C.c_int, vp, C.POINTER(i64), vp]),

@@ -39,9 +39,53 @@ int num_sms() {
   return sms;
 }
 
+// ---- per-stage profiling
+static bool g_prof_on = false;
+struct ProfPair { cudaEvent_t a, b; int tag; };
+static std::vector<ProfPair> g_prof_pairs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t g_prof_open[kProfTags];
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof_on || tag < 0 || tag >= kProfTags) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, st);
+  g_prof_open[tag] = e;
+}
+void prof_end(int tag, cudaStream_t st) {
+  if (!g_prof_on || tag < 0 || tag >= kProfTags || !g_prof_open[tag]) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, st);
+  g_prof_pairs.push_back({g_prof_open[tag], e, tag});
+  g_prof_open[tag] = nullptr;
+}
+
 }  // namespace lcrec
 
 using namespace lcrec;
+
+extern "C" int lcrec_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return LCREC_OK;
+}
+// Synchronises, then adds the elapsed ms of every recorded pair to ms[tag] and the pair count to
+// calls[tag] (both arrays of 32 entries, host memory); clears the record.
+extern "C" int lcrec_profile_collect(double* ms, int64_t* calls) {
+  LC_ARG(ms && calls);
+  LC_CUDA(cudaDeviceSynchronize());
+  for (auto& p : g_prof_pairs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) { ms[p.tag] += t; calls[p.tag] += 1; }
+    g_prof_pool.push_back(p.a); g_prof_pool.push_back(p.b);
+  }
+  g_prof_pairs.clear();
+  (void)cudaGetLastError();
+  return LCREC_OK;
+}
 
 extern "C" int lcrec_version(void) { return 100; }
 
@@ -161,6 +205,7 @@ extern "C" int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t 
   for (int64_t s = 0; s < n; s += ix->chunk_rows) {
     const int64_t m = std::min(ix->chunk_rows, n - s);
     LC_TRY(lcrec_mlp_forward(ix->enc, x + s * ix->in_dim, m, ix->z, nullptr, ix->mlp_ws, ix->mlp_ws_bytes, stream));
+    ProfScope prof(20, (cudaStream_t)stream);
     LC_TRY(lcrec_rq_quantize(ix->z, m, ix->D, ix->L, ix->cb.data(), ix->K.data(), ix->L, ix->L - 1,
                              ix->codes + (row_offset + s) * ix->L, nullptr, ix->resid + (row_offset + s) * ix->D,
                              nullptr, stream));
@@ -170,13 +215,17 @@ extern "C" int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t 
 
 // One check (+ resolve when `resolve`): counts_host receives [n_unique, n_groups, rows, max_mult, flags]
 static int indexer_check(lcrec_indexer_t* ix, int64_t n, bool resolve, int64_t* counts_host, cudaStream_t st) {
-  LC_TRY(lcrec_collisions(ix->codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
-                          ix->col_ws_bytes, st));
+  {
+    ProfScope prof(21, st);
+    LC_TRY(lcrec_collisions(ix->codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
+                            ix->col_ws_bytes, st));
+  }
   LC_CUDA(cudaMemsetAsync(ix->flags, 0, sizeof(int32_t) * 2, st));
   LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 5, cudaMemcpyDeviceToHost, st));
   LC_CUDA(cudaStreamSynchronize(st));
   const int64_t groups = ix->counts_host[1], rows = ix->counts_host[2];
   if (resolve && groups > 0) {
+    ProfScope prof(22, st);
     LC_TRY(lcrec_sinkhorn_groups(ix->resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
                                  ix->counts + 1, groups, rows, ix->eps, ix->iters, ix->codes, ix->L, ix->L - 1,
                                  ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));

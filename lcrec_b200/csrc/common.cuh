@@ -53,6 +53,17 @@ inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 
 int num_sms();
 
+// Optional per-stage device timing (CUDA events on the launching stream), used by bench.py for the
+// live roofline figure.  Tags: 0 = split, 1..16 = MLP layer l, 20 = rq, 21 = collide, 22 = sinkhorn.
+constexpr int kProfTags = 32;
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+struct ProfScope {
+  int tag; cudaStream_t st;
+  ProfScope(int t, cudaStream_t s) : tag(t), st(s) { prof_begin(tag, st); }
+  ~ProfScope() { prof_end(tag, st); }
+};
+
 // bump allocator over a caller-provided workspace
 struct Arena {
   char* base; int64_t size; int64_t off;

@@ -37,6 +37,18 @@ def launch_count() -> int:
     return int(_lib.load().lcrec_launch_count())
 
 
+def profile_enable(on: bool) -> None:
+    _lib.check(_lib.load().lcrec_profile_enable(int(on)))
+
+
+def profile_collect() -> dict:
+    """{tag: (ms, calls)} accumulated since the last collect (synchronises the device)."""
+    ms = (C.c_double * 32)()
+    calls = (C.c_int64 * 32)()
+    _lib.check(_lib.load().lcrec_profile_collect(ms, calls))
+    return {t: (ms[t], int(calls[t])) for t in range(32) if calls[t]}
+
+
 # --------------------------------------------------------------------------- MLP
 class MlpHandle:
     """Prepared (3xTF32-split) weights of one MLPLayers stack."""
@@ -103,7 +115,7 @@ class MlpHandle:
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool,
-                   acc_chunk: int = 0, variant: int = 0) -> torch.Tensor:
+                   acc_chunk: int = 64, variant: int = 0) -> torch.Tensor:
     """relu?(x @ w.T + b) with the 3xTF32 tcgen05 kernel (nn.Linear, layers.py:23)."""
     _need_cuda(x, w)
     lib = _lib.load()
@@ -230,7 +242,7 @@ def sort_codes(codes: torch.Tensor, n_codes: Sequence[int]):
 
 def sinkhorn_groups(resid: torch.Tensor, codebook: torch.Tensor, offsets: torch.Tensor, members: torch.Tensor,
                     n_groups_dev: torch.Tensor, max_groups: int, max_rows: int, epsilon: float, iters: int,
-                    codes: torch.Tensor, level: int) -> int:
+                    codes: torch.Tensor, level: int, part_mod: int = 1, part_rem: int = 0) -> int:
     """Per-group Sinkhorn re-assignment of ``codes[:, level]`` in place; returns the flag word."""
     _need_cuda(resid, codebook, offsets, members, codes)
     lib = _lib.load()
@@ -239,10 +251,10 @@ def sinkhorn_groups(resid: torch.Tensor, codebook: torch.Tensor, offsets: torch.
     flags = torch.zeros(2, dtype=torch.int32, device=r.device)
     ws = _ws(lib.lcrec_sinkhorn_groups_workspace_bytes(max_rows, cb.shape[0]), r.device)
     with torch.cuda.device(r.device):
-        _lib.check(lib.lcrec_sinkhorn_groups(_p(r), cb.shape[1], _p(cb), cb.shape[0], _p(offsets), _p(members),
-                                             _p(n_groups_dev), int(max_groups), int(max_rows), float(epsilon), int(iters),
-                                             _p(codes), codes.shape[1], int(level), _p(flags), _p(ws), ws.numel(),
-                                             _stream(r)))
+        _lib.check(lib.lcrec_sinkhorn_groups_part(_p(r), cb.shape[1], _p(cb), cb.shape[0], _p(offsets), _p(members),
+                                                  _p(n_groups_dev), int(max_groups), int(max_rows), float(epsilon),
+                                                  int(iters), _p(codes), codes.shape[1], int(level), int(part_mod),
+                                                  int(part_rem), _p(flags), _p(ws), ws.numel(), _stream(r)))
     return int(flags[0].item())
 
 

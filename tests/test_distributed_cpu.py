@@ -1,0 +1,80 @@
+"""world_size-2 gloo test of the sharded generation host logic (lcrec_b200.distributed) on CPU.
+The per-rank arithmetic is supplied by an oracle-backed stand-in backend (tests only); what is under
+test is the shard plan, the ragged all-gather, the group partition and the delta all-reduce."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lcrec_b200.distributed import ShardPlan, generate_codes_sharded
+from oracle import lcrec_oracle as O
+from tests.conftest import GOLDEN, state_dict_of
+
+
+class OracleBackend:
+    def __init__(self, p):
+        self.p = p
+        self.p_sk = O.RqvaeParams(encoder=p.encoder, codebooks=p.codebooks, sk_epsilons=O.generation_epsilons(p),
+                                  sk_iters=p.sk_iters, beta=p.beta)
+
+    def pass0(self, x_local):
+        z = O.mlp_forward(x_local.numpy(), self.p.encoder)
+        resids, _, codes = O.rq_trace(z, self.p)
+        return torch.from_numpy(codes), torch.from_numpy(resids[-1])
+
+    def collisions(self, codes_all):
+        c = codes_all.numpy()
+        groups = sorted(O.collision_groups(c), key=lambda g: tuple(c[g[0]]))
+        return {"groups": groups, "n_groups": len(groups), "n_rows": sum(map(len, groups)), "n_unique": O.n_unique_codes(c),
+                "max_multiplicity": O.max_conflicts(c)}
+
+    def resolve(self, resid_all, codes_all, info, mod, rem):
+        r = resid_all.numpy()
+        for gi, g in enumerate(info["groups"]):
+            if gi % mod == rem:
+                codes_all[g, -1] = torch.from_numpy(O.vq_assign(r[g], self.p.codebooks[-1], True, self.p_sk.sk_epsilons[-1], self.p.sk_iters))
+
+
+def _load():
+    with np.load(os.path.join(GOLDEN, "small_model.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    p = O.params_from_state_dict(state_dict_of(g), g["sk_epsilons"].tolist(), int(g["sk_iters"]))
+    return g["x"][:701], p          # odd count: ragged shards
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, p = _load()
+    plan = ShardPlan(x.shape[0], world)
+    codes, stats = generate_codes_sharded(OracleBackend(p), torch.from_numpy(x[plan.slice(rank)]), plan, rank, max_rounds=20)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, codes.numpy())
+    if rank == 0:
+        np.save(out, np.concatenate(gathered))
+    dist.destroy_process_group()
+
+
+def test_shard_plan():
+    plan = ShardPlan(10, 4)
+    assert [plan.count(r) for r in range(4)] == [3, 3, 2, 2]
+    assert [plan.start(r) for r in range(4)] == [0, 3, 6, 8] and plan.max_count == 3
+    assert ShardPlan(8, 8).slice(7) == slice(7, 8)
+
+
+def test_two_rank_generation_equals_single_process(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "codes.npy")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    x, p = _load()
+    ref, _ = O.generate_indices(x, p, batch_size=x.shape[0], reencode=False)
+    assert got.shape == ref.shape
+    assert (got != ref).any(axis=1).sum() <= 2      # GEMM batch-shape rounding between 701 rows and 351/350 rows
+    assert O.n_unique_codes(got) == O.n_unique_codes(ref)
