@@ -263,11 +263,15 @@ def run_gpu_arm(a):
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if a.profile_window:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(a.steps):
         codes, stats = step()
     e1.record()
     barrier()
+    if a.profile_window:
+        torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     launches = ops.launch_count() - launches0
@@ -351,6 +355,8 @@ def main():
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=2048)
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--profile-window", dest="profile_window", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
     if a.impl == "reference":

@@ -493,9 +493,10 @@ extern "C" int64_t lcrec_linear_workspace_bytes(int64_t n_rows, int k_in, int n_
 extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* w, const float* b,
                                     int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,
                                     int64_t ws_bytes, void* stream) {
-  LC_ARG(x && w && y && n_rows >= 0 && k_in > 0 && n_out > 0);
+  LC_ARG(n_rows >= 0 && k_in > 0 && n_out > 0);
   LC_TRY(lcrec_device_check());
   if (n_rows == 0) return LCREC_OK;
+  LC_ARG(x && w && y);
   LC_ARG((n_out & 3) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);

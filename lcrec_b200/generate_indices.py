@@ -41,9 +41,9 @@ def build_indexer(model: RQVAE, max_items: int, chunk_rows: int = 131072) -> ops
     model.eval()
     eps = apply_generation_epsilons(model)
     with torch.no_grad():
+        if not model.encoder._fused_ok():
+            raise RuntimeError("encoder must be a ReLU MLP in eval mode for index generation")
         handle = model.encoder._get_handle()
-    if not model.encoder._fused_ok():
-        raise RuntimeError("encoder must be ReLU MLP in eval mode for index generation")
     cbs = [vq.embedding.weight.detach() for vq in model.rq.vq_layers]
     return ops.Indexer(handle, cbs, eps, model.rq.vq_layers[-1].sk_iters, max_items, chunk_rows)
 

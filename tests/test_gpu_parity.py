@@ -58,7 +58,7 @@ def test_linear_matches_fp64(n, k, m, relu):
         t32 = torch.nn.functional.linear(x, w, b)
         t32 = t32.clamp_min(0) if relu else t32
         err32 = (t32.double() - ref).abs().mean().item()
-        assert (y.double() - ref).abs().mean().item() <= 2.0 * err32 + 1e-9 * scale
+        assert (y.double() - ref).abs().mean().item() <= max(3.0 * err32, 2e-7 * scale)
 
 
 def test_linear_zero_rows_and_errors():
