@@ -119,6 +119,10 @@ int lcrec_sinkhorn_groups_part(const float* resid, int e_dim, const float* codeb
                                int64_t* codes, int n_levels, int level, int part_mod, int part_rem,
                                int32_t* flags, void* ws, int64_t ws_bytes, void* stream);
 
+/* Arithmetic form of the per-group Sinkhorn: 0 (default) = scaling-vector iterations with the literal
+ * last column step; 1 = the reference's in-place divides everywhere (verification mode, ~10x slower). */
+int lcrec_sinkhorn_set_mode(int literal);
+
 /* ---- a12/a14: collision bookkeeping (generate_indices.py:18-42, trainer.py:141-150) -----
  * Packs (n, L) int64 codes into u64 keys, radix-sorts (key, item) and emits collision groups
  * in CSR form: groups ordered by key, members ascending (the reference orders groups by

@@ -37,6 +37,11 @@ def launch_count() -> int:
     return int(_lib.load().lcrec_launch_count())
 
 
+def sinkhorn_set_mode(literal: bool) -> None:
+    """True = literal in-place divides in the group kernels (verification); False = fast form (default)."""
+    _lib.check(_lib.load().lcrec_sinkhorn_set_mode(int(literal)))
+
+
 def profile_enable(on: bool) -> None:
     _lib.check(_lib.load().lcrec_profile_enable(int(on)))
 

@@ -182,6 +182,41 @@ def test_sinkhorn_groups_match_oracle():
     assert bad == 0, (bad, rows)
 
 
+@pytest.mark.parametrize("k,d", [(256, 32), (32, 16), (100, 32), (512, 32)])
+def test_sinkhorn_groups_fast_form_equals_literal(k, d):
+    """Scaling-vector kernels (warp-per-group / CTA) vs the literal in-place-divide kernel on 30k realistic
+    groups: near-duplicate rows (exact-tie regime), sizes 2..12 plus a few large ones."""
+    rng = np.random.default_rng(11)
+    sizes = np.concatenate([rng.integers(2, 13, size=30000), [40, 99, 100, 150]])
+    n_items = int(sizes.sum())
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    centres = (rng.standard_normal((len(sizes), d)) * 0.05).astype(np.float32)
+    resid = np.repeat(centres, sizes, axis=0) + (rng.standard_normal((n_items, d)) * 0.003).astype(np.float32)
+    dup = rng.integers(0, n_items - 1, size=2000)
+    same_group = np.searchsorted(off, dup, side="right") == np.searchsorted(off, dup + 1, side="right")
+    resid[dup[same_group] + 1] = resid[dup[same_group]]                 # exact duplicates inside groups
+    cb = (rng.standard_normal((k, d)) * 0.05).astype(np.float32)
+    mem = rng.permutation(n_items).astype(np.int64)
+    for g in range(len(sizes)):
+        mem[off[g]:off[g + 1]].sort()
+    resid_items = np.empty_like(resid)
+    resid_items[mem] = resid
+    out = []
+    for literal in (True, False):
+        ops.sinkhorn_set_mode(literal)
+        codes = torch.zeros((n_items, 4), dtype=torch.int64, device=DEV)
+        fl = ops.sinkhorn_groups(T(resid_items), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV),
+                                 len(sizes), n_items, 0.003, 50, codes, 3)
+        assert fl == 0
+        out.append(codes.cpu().numpy()[:, 3])
+    ops.sinkhorn_set_mode(False)
+    assert (out[0] != out[1]).sum() == 0, int((out[0] != out[1]).sum())
+    # spot-check the literal kernel against the numpy oracle on the first 200 groups
+    for g in range(200):
+        rows = mem[off[g]:off[g + 1]]
+        assert (out[0][rows] == O.vq_assign(resid_items[rows], cb, True, 0.003, 50)).all()
+
+
 # ------------------------------------------------------------------ a12/a14: collisions
 @pytest.mark.parametrize("n,k,L", [(0, 16, 3), (1, 16, 3), (5, 4, 2), (10000, 16, 3), (100000, 256, 4), (70000, 8192, 4),
                                    (4097, 65536, 4)])
