@@ -37,9 +37,20 @@ def launch_count() -> int:
     return int(_lib.load().lcrec_launch_count())
 
 
-def sinkhorn_set_mode(literal: bool) -> None:
-    """True = literal in-place divides in the group kernels (verification); False = fast form (default)."""
-    _lib.check(_lib.load().lcrec_sinkhorn_set_mode(int(literal)))
+def sinkhorn_set_mode(mode: int) -> None:
+    """0 = literal order with exactly rounded fast divides (default), 1 = literal with IEEE divides
+    (verification), 2 = scaling-vector form."""
+    _lib.check(_lib.load().lcrec_sinkhorn_set_mode(int(mode)))
+
+
+def div_selftest(x: torch.Tensor, y: torch.Tensor):
+    """(mismatches vs IEEE x / y, operand pairs that took the fast path) for the exact-division helper."""
+    _need_cuda(x, y)
+    bad, fast = C.c_int64(), C.c_int64()
+    x2, y2 = x.double().contiguous(), y.double().contiguous()
+    with torch.cuda.device(x2.device):
+        _lib.check(_lib.load().lcrec_div_selftest(_p(x2), _p(y2), x2.numel(), C.byref(bad), C.byref(fast), _stream(x2)))
+    return int(bad.value), int(fast.value)
 
 
 def profile_enable(on: bool) -> None:
