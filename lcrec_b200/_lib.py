@@ -44,7 +44,6 @@ SIGNATURES = {
     "lcrec_sinkhorn_groups_part": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, f64, C.c_int, vp, C.c_int,
                                              C.c_int, C.c_int, C.c_int, vp, vp, i64, vp]),
     "lcrec_sinkhorn_set_mode": (C.c_int, [C.c_int]),
-    "lcrec_div_selftest": (C.c_int, [vp, vp, i64, C.POINTER(i64), C.POINTER(i64), vp]),
     "lcrec_collisions_workspace_bytes": (i64, [i64]),
     "lcrec_collisions": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, vp, i64, vp]),
     "lcrec_sort_codes": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, i64, vp]),

@@ -38,19 +38,8 @@ def launch_count() -> int:
 
 
 def sinkhorn_set_mode(mode: int) -> None:
-    """0 = literal order with exactly rounded fast divides (default), 1 = literal with IEEE divides
-    (verification), 2 = scaling-vector form."""
+    """0 = literal in-place divides (default, bit-faithful); 1 = scaling-vector form (fast)."""
     _lib.check(_lib.load().lcrec_sinkhorn_set_mode(int(mode)))
-
-
-def div_selftest(x: torch.Tensor, y: torch.Tensor):
-    """(mismatches vs IEEE x / y, operand pairs that took the fast path) for the exact-division helper."""
-    _need_cuda(x, y)
-    bad, fast = C.c_int64(), C.c_int64()
-    x2, y2 = x.double().contiguous(), y.double().contiguous()
-    with torch.cuda.device(x2.device):
-        _lib.check(_lib.load().lcrec_div_selftest(_p(x2), _p(y2), x2.numel(), C.byref(bad), C.byref(fast), _stream(x2)))
-    return int(bad.value), int(fast.value)
 
 
 def profile_enable(on: bool) -> None:

@@ -47,9 +47,7 @@ for (lo, hi, ng) in [(2, 2, 200000), (3, 4, 100000), (5, 8, 60000), (9, 24, 2000
     rng = np.random.default_rng(lo)
     sizes = rng.integers(lo, hi + 1, size=ng)
     resid, cb, off, mem = make(sizes, 32, 256, lo)
-    lit, t_lit = run(resid, cb, off, mem, 1)
-    dflt, t_dflt = run(resid, cb, off, mem, 0)
-    fast, t_fast = run(resid, cb, off, mem, 2)
-    print(json.dumps(dict(kind="class", lo=lo, hi=hi, groups=ng, rows=int(off[-1]), ms_ieee_literal=t_lit, ms_default=t_dflt,
-                          ms_scaling=t_fast, us_per_group_default=t_dflt * 1e3 / ng, default_vs_ieee_mismatch=int((lit != dflt).sum()))), flush=True)
+    lit, t_lit = run(resid, cb, off, mem, 0)
+    fast, t_fast = run(resid, cb, off, mem, 1)
+    print(json.dumps(dict(kind="class", lo=lo, hi=hi, groups=ng, rows=int(off[-1]), ms_literal=t_lit, ms_scaling=t_fast)), flush=True)
     classify(resid, cb, off, mem, lit, fast, f"scaling {lo}-{hi}")
