@@ -120,9 +120,12 @@ int lcrec_sinkhorn_groups_part(const float* resid, int e_dim, const float* codeb
                                int32_t* flags, void* ws, int64_t ws_bytes, void* stream);
 
 /* Arithmetic form of the per-group Sinkhorn kernels:
- *   0 (default) the reference's literal in-place divides (layers.py:93-107): bit-faithful plan;
- *   1           scaling-vector iterations + literal last column step (fastest; ulp-level ties of Q may
- *               resolve differently: 0 of 1.7 M rows on realistic data, ~1e-5 on duplicate-heavy data). */
+ *   0  the reference's literal in-place divides (layers.py:93-107) for every group: bit-faithful plan;
+ *   1  scaling-vector iterations + literal last column step (fastest; ulp-level ties of Q may resolve
+ *      differently: 0 of 1.7 M rows on realistic data, ~1e-5 on duplicate-heavy data);
+ *   2  (default) filtered: form 1 for groups of <= 8 rows, then every group whose argmax is not provably the
+ *      literal kernel's (lead <= 1e-9 relative and not a robust exact tie) is re-run with form 0; larger
+ *      groups always use form 0.  Same codes as mode 0 (tested), close to the speed of mode 1. */
 int lcrec_sinkhorn_set_mode(int mode);
 
 /* ---- a12/a14: collision bookkeeping (generate_indices.py:18-42, trainer.py:141-150) -----

@@ -38,7 +38,8 @@ def launch_count() -> int:
 
 
 def sinkhorn_set_mode(mode: int) -> None:
-    """0 = literal in-place divides (default, bit-faithful); 1 = scaling-vector form (fast)."""
+    """0 = literal in-place divides everywhere; 1 = scaling-vector form; 2 = filtered hybrid (default):
+    scaling form + literal re-run of every group whose argmax is not provably the literal one."""
     _lib.check(_lib.load().lcrec_sinkhorn_set_mode(int(mode)))
 
 
@@ -247,8 +248,9 @@ def sort_codes(codes: torch.Tensor, n_codes: Sequence[int]):
 
 def sinkhorn_groups(resid: torch.Tensor, codebook: torch.Tensor, offsets: torch.Tensor, members: torch.Tensor,
                     n_groups_dev: torch.Tensor, max_groups: int, max_rows: int, epsilon: float, iters: int,
-                    codes: torch.Tensor, level: int, part_mod: int = 1, part_rem: int = 0) -> int:
-    """Per-group Sinkhorn re-assignment of ``codes[:, level]`` in place; returns the flag word."""
+                    codes: torch.Tensor, level: int, part_mod: int = 1, part_rem: int = 0, want_risky: bool = False):
+    """Per-group Sinkhorn re-assignment of ``codes[:, level]`` in place; returns the flag word (and, on
+    request, how many groups the filtered mode re-ran through the literal kernel)."""
     _need_cuda(resid, codebook, offsets, members, codes)
     lib = _lib.load()
     assert codes.dtype == torch.int64 and codes.is_contiguous()
@@ -260,6 +262,9 @@ def sinkhorn_groups(resid: torch.Tensor, codebook: torch.Tensor, offsets: torch.
                                                   _p(n_groups_dev), int(max_groups), int(max_rows), float(epsilon),
                                                   int(iters), _p(codes), codes.shape[1], int(level), int(part_mod),
                                                   int(part_rem), _p(flags), _p(ws), ws.numel(), _stream(r)))
+    if want_risky:   # the library keeps its cursor words at the start of the workspace: [big cursor u64][risky count i32]
+        off = (-ws.data_ptr()) % 256
+        return int(flags[0].item()), int(ws[off + 8: off + 12].view(torch.int32).item())
     return int(flags[0].item())
 
 

@@ -12,12 +12,12 @@ def run(resid_items, cb, off, mem, mode):
     n_items = resid_items.shape[0]
     codes = torch.zeros((n_items, 4), dtype=torch.int64, device=dev)
     args = (T(resid_items), T(cb), T(off), T(mem), torch.tensor([len(off) - 1], device=dev), len(off) - 1, int(off[-1]), 0.003, 50, codes, 3)
-    ops.sinkhorn_groups(*args)
+    _, risky = ops.sinkhorn_groups(*args, want_risky=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); ops.sinkhorn_groups(*args); e1.record(); torch.cuda.synchronize()
-    ops.sinkhorn_set_mode(0)
-    return codes.cpu().numpy()[:, 3], e0.elapsed_time(e1)
+    ops.sinkhorn_set_mode(2)
+    return codes.cpu().numpy()[:, 3], e0.elapsed_time(e1), risky
 
 def make(sizes, d, k, seed, noise=0.003):
     rng = np.random.default_rng(seed)
@@ -43,11 +43,15 @@ def classify(resid, cb, off, mem, lit, fast, tag):
                         oracle=int(np.argmax(q[i])), b_over_k=len(rows) / cb.shape[0]))
     print(json.dumps(dict(kind="mismatch", tag=tag, total_rows=int(len(lit)), n_bad=int(len(bad)), detail=out)), flush=True)
 
-for (lo, hi, ng) in [(2, 2, 200000), (3, 4, 100000), (5, 8, 60000), (9, 24, 20000), (25, 99, 3000), (100, 300, 300)]:
+for (lo, hi, ng, noise) in [(2, 2, 200000, 0.003), (3, 4, 100000, 0.003), (5, 8, 60000, 0.003), (9, 24, 20000, 0.003),
+                            (2, 8, 150000, 1e-4), (2, 8, 150000, 1e-6), (2, 8, 150000, 0.0)]:
     rng = np.random.default_rng(lo)
     sizes = rng.integers(lo, hi + 1, size=ng)
-    resid, cb, off, mem = make(sizes, 32, 256, lo)
-    lit, t_lit = run(resid, cb, off, mem, 0)
-    fast, t_fast = run(resid, cb, off, mem, 1)
-    print(json.dumps(dict(kind="class", lo=lo, hi=hi, groups=ng, rows=int(off[-1]), ms_literal=t_lit, ms_scaling=t_fast)), flush=True)
-    classify(resid, cb, off, mem, lit, fast, f"scaling {lo}-{hi}")
+    resid, cb, off, mem = make(sizes, 32, 256, lo, noise)
+    lit, t_lit, _ = run(resid, cb, off, mem, 0)
+    fast, t_fast, _ = run(resid, cb, off, mem, 1)
+    hyb, t_hyb, risky = run(resid, cb, off, mem, 2)
+    print(json.dumps(dict(kind="class", lo=lo, hi=hi, groups=ng, rows=int(off[-1]), ms_literal=t_lit, ms_scaling=t_fast,
+                          ms_filtered=t_hyb, risky_groups=risky, filtered_vs_literal_mismatch=int((hyb != lit).sum()),
+                          scaling_vs_literal_mismatch=int((fast != lit).sum()))), flush=True)
+    classify(resid, cb, off, mem, lit, hyb, f"filtered {lo}-{hi} noise {noise}")

@@ -181,22 +181,22 @@ def test_sinkhorn_groups_match_oracle():
         bad += int((got[g, 3] != idx).sum()); rows += len(g)
     assert bad == 0, (bad, rows)
     # the same through the other two arithmetic modes
-    for mode, tol in ((1, 3),):
+    for mode, tol in ((0, 0), (1, 3)):
         try:
             ops.sinkhorn_set_mode(mode)
             c2 = torch.full((n_items, 4), 7, dtype=torch.int64, device=DEV)
             ops.sinkhorn_groups(T(resid), T(cb), T(off), T(mem), torch.tensor([len(groups)], device=DEV),
                                 len(groups), int(off[-1]), 0.003, 50, c2, 3)
         finally:
-            ops.sinkhorn_set_mode(0)
+            ops.sinkhorn_set_mode(2)
         assert int((c2.cpu().numpy() != got).sum()) <= tol, mode
 
 
 @pytest.mark.parametrize("k,d", [(256, 32), (32, 16), (100, 32), (512, 32)])
 def test_sinkhorn_group_modes_agree(k, d):
-    """Scaling-vector kernels (warp-per-group / CTA) against the default literal kernels on 30k groups in the
-    exact-tie regime (near-duplicate + duplicate rows, sizes 2..12 plus a few large): the scaling form may
-    differ on ulp-level ties only (counted, < 1e-4 of rows)."""
+    """The three arithmetic modes on 30k groups in the exact-tie regime (near-duplicate + duplicate rows, sizes
+    2..12 plus a few large): the default filtered mode (2) must give exactly the codes of the all-literal
+    mode (0); the pure scaling form (1) may differ on ulp-level ties only (counted, < 1e-4 of rows)."""
     rng = np.random.default_rng(11)
     sizes = np.concatenate([rng.integers(2, 13, size=30000), [40, 99, 100, 150]])
     n_items = int(sizes.sum())
@@ -214,7 +214,7 @@ def test_sinkhorn_group_modes_agree(k, d):
     resid_items[mem] = resid
     out = {}
     try:
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             ops.sinkhorn_set_mode(mode)
             codes = torch.zeros((n_items, 4), dtype=torch.int64, device=DEV)
             fl = ops.sinkhorn_groups(T(resid_items), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV),
@@ -222,21 +222,23 @@ def test_sinkhorn_group_modes_agree(k, d):
             assert fl == 0
             out[mode] = codes.cpu().numpy()[:, 3]
     finally:
-        ops.sinkhorn_set_mode(0)
+        ops.sinkhorn_set_mode(2)
+    assert (out[2] != out[0]).sum() == 0, int((out[2] != out[0]).sum())
     assert (out[1] != out[0]).mean() < 1e-4
-    # spot-check against the numpy oracle on the first 300 groups.  Groups that contain exact duplicate rows sit
-    # in the exact-tie regime where even the summation order inside a row sum decides ulp-level ties (torch-CPU
-    # and torch-CUDA differ there too); everywhere else the codes must be identical.
-    bad = rows_n = 0
+    # spot-check against the numpy oracle on the first 300 groups.  The oracle's fp32 distances come from a
+    # BLAS matmul, the kernel's from FMA chains (2e-7 relative apart); exp(-d/eps) amplifies that 333x, so a
+    # differing row is accepted only if the oracle's own plan has the two candidates within 2e-4 relative
+    # (a counted near-tie), and such rows must be rare.
+    near = rows_n = 0
     for g in range(300):
         rows = mem[off[g]:off[g + 1]]
-        ref = O.vq_assign(resid_items[rows], cb, True, 0.003, 50)
-        has_dup = len(np.unique(resid_items[rows], axis=0)) < len(rows)
-        if has_dup:
-            bad += int((out[0][rows] != ref).sum()); rows_n += len(rows)
-        else:
-            assert (out[0][rows] == ref).all(), g
-    assert bad <= max(1, rows_n // 20), (bad, rows_n)
+        idx, _, q = O.vq_assign(resid_items[rows], cb, True, 0.003, 50, want_q=True)
+        for i in np.nonzero(out[0][rows] != idx)[0]:
+            a_, b_ = q[i, idx[i]], q[i, out[0][rows][i]]
+            assert abs(a_ - b_) <= 2e-4 * abs(a_), (g, i, a_, b_)
+            near += 1
+        rows_n += len(rows)
+    assert near <= max(2, rows_n // 200), (near, rows_n)
 
 
 # ------------------------------------------------------------------ a12/a14: collisions
