@@ -58,9 +58,13 @@ int lcrec_mlp_forward(lcrec_mlp_t* mlp, const float* x, int64_t n_rows, float* y
 int lcrec_mlp_set_acc_chunk(lcrec_mlp_t* mlp, int k_elems);
 /* tile variant for experiments: 0 = default (N tile 256: K block 16 x 4 stages), 1 = K block 32 x 2 stages */
 int lcrec_mlp_set_variant(lcrec_mlp_t* mlp, int variant);
+/* operand encoding of the GEMMs: 0 = tf32 x3 (fp32 operands split into two tf32 numbers), 1 = f16 x3 (per-row
+ * power-of-two scale, two fp16 numbers; same 22-bit operand precision, twice the tensor rate). */
+int lcrec_mlp_set_engine(lcrec_mlp_t* mlp, int engine);
 int lcrec_mlp_in_dim(const lcrec_mlp_t* mlp);
 int lcrec_mlp_out_dim(const lcrec_mlp_t* mlp);
-/* One nn.Linear (+ReLU) on raw fp32 operands (layers.py:23): splits x and w on the fly into ws. */
+/* One nn.Linear (+ReLU) on raw fp32 operands (layers.py:23): splits x and w on the fly into ws.
+ * variant: bit 0 = alternative tile for wide N, bit 1 = f16 x3 engine. */
 int64_t lcrec_linear_workspace_bytes(int64_t n_rows, int k_in, int n_out);
 int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* w, const float* b,
                          int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,

@@ -15,10 +15,18 @@
 // fold finished chunks into fp32 registers with round-to-nearest adds while the next chunk is
 // being multiplied (two TMEM buffers = the chunks ping-pong).
 //
+// Two operand encodings share the kernel (template F16):
+//   tf32 x3  operands fp32 in memory, each value a tf32 number; MMA kind::tf32 (K = 8 per instruction);
+//   f16  x3  operands fp16 with a per-row power-of-two scale s: h = fp16(x s), l = fp16(x s - h); MMA kind::f16
+//            (K = 16 per instruction, twice the tensor rate).  h + l carries 22 significant bits for every
+//            element within 2^-18 of its row maximum and an absolute error <= 2^-40 of the row maximum below
+//            that; hi*hi products are exact in fp32.  The epilogue multiplies by 1/(s_row s_col).
+//
 // CTA = 10 warps: warps 0-7 fold/epilogue (TMEM -> registers -> bias/ReLU/split -> global),
 // warp 8 = TMA producer (one lane), warp 9 = TMEM allocator + MMA issuer (one lane).
 // Tile: 128 rows x BN columns, K block = BK fp32 (BK*4 bytes = swizzle span).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 #include <vector>
@@ -39,36 +47,40 @@ struct LinearArgs {
   const float* bias;  // (n_out) or null
   float* y;           // (n_rows, ldy) fp32 or null
   int64_t ldy;
-  float* y_hi;        // split output for the next layer, or null
+  float* y_hi;        // split output for the next layer, or null (tf32 engine only)
   float* y_lo;
   int64_t ld_split;
+  const float* row_scale;   // f16 engine: 1 / s_row (n_rows) and 1 / s_col (n_out); null = 1
+  const float* col_scale;
 };
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 320;
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, bool F16 = false>
 struct LinearCfg {
-  static constexpr int A_BYTES = kTileM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int ELEM = F16 ? 2 : 4;
+  static constexpr int KSTEP = 32 / ELEM;              // elements per MMA instruction (32 bytes of K)
+  static constexpr int A_BYTES = kTileM * BK * ELEM;
+  static constexpr int B_BYTES = BN * BK * ELEM;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr uint32_t ROW_BYTES = BK * 4;        // 128 or 64
+  static constexpr uint32_t ROW_BYTES = BK * ELEM;     // 128 or 64
   static constexpr uint32_t SBO = 8 * ROW_BYTES;
   static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? 2u : (ROW_BYTES == 64 ? 4u : 6u);
-  static_assert(BK == 32 || BK == 16, "BK*4 must be a 128B or 64B swizzle span");
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "a K block must span a 128B or 64B swizzle row");
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
-linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+linear_split3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                      const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                      const LinearArgs args, const int tiles_n) {
-  using C = LinearCfg<BN, BK, STAGES>;
+  using C = LinearCfg<BN, BK, STAGES, F16>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -126,7 +138,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(kTileM, BN, 2);
+      constexpr uint32_t idesc = umma_idesc(kTileM, BN, F16 ? 0 : 2);
       int kb = 0;
       for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
@@ -146,12 +158,18 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
           const uint64_t d_bhi = umma_smem_desc(a_hi + 2 * C::A_BYTES, C::SBO, C::LAYOUT);
           const uint64_t d_blo = umma_smem_desc(a_hi + 2 * C::A_BYTES + C::B_BYTES, C::SBO, C::LAYOUT);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // 8 tf32 = 32 bytes along K
+          for (int k = 0; k < BK / C::KSTEP; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);   // one MMA consumes 32 bytes along K
             // small cross terms first, then the dominant hi*hi product
-            umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, first ? 0u : 1u);
-            umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
-            umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            if constexpr (F16) {
+              umma_f16(d_tmem, d_alo + adv, d_bhi + adv, idesc, first ? 0u : 1u);
+              umma_f16(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_f16(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, d_alo + adv, d_bhi + adv, idesc, first ? 0u : 1u);
+              umma_tf32(d_tmem, d_ahi + adv, d_blo + adv, idesc, 1u);
+              umma_tf32(d_tmem, d_ahi + adv, d_bhi + adv, idesc, 1u);
+            }
             first = false;
           }
           umma_commit(empty_bar(s));   // smem slot reusable once these MMAs have read it
@@ -191,6 +209,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
     const int64_t row = tile_m * kTileM + q * 32 + lane;
     const int col_base = tile_n * BN + half * NCOL;
     if (row < args.n_rows) {
+      const float rscale = args.row_scale ? __ldg(args.row_scale + row) : 1.f;
 #pragma unroll
       for (int j = 0; j < NCOL; j += 4) {
         const int col = col_base + j;
@@ -199,6 +218,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float t = acc[j + i];
+          if constexpr (F16) { if (col + i < args.n_out) t = (t * rscale) * (args.col_scale ? __ldg(args.col_scale + col + i) : 1.f); }
           if (args.bias != nullptr && col + i < args.n_out) t += __ldg(args.bias + col + i);
           if (args.relu) t = fmaxf(t, 0.f);
           v[i] = t;
@@ -254,6 +274,62 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, int64_t rows, int
   }
 }
 
+// x (rows, k) fp32 -> per-row power-of-two scale s with max|x s| in [2^14, 2^15), hi = fp16(x s),
+// lo = fp16(x s - hi) (both padded with zeros to ld_out), inv_scale[row] = 1 / s.  One warp per row, two
+// passes over the row (the second one hits L1/L2).
+__global__ void __launch_bounds__(256) split_f16_rows_kernel(const float* __restrict__ x, int64_t rows, int k, int64_t ldx,
+                                                             __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld_out,
+                                                             float* __restrict__ inv_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec_ok = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + r * ldx;
+    float m = 0.f;
+    if (vec_ok) {
+      for (int c = lane * 4; c + 3 < k; c += 128) {
+        const float4 t = *reinterpret_cast<const float4*>(xr + c);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+      }
+      for (int c = (k & ~3) + lane; c < k; c += 32) m = fmaxf(m, fabsf(xr[c]));
+    } else {
+      for (int c = lane; c < k; c += 32) m = fmaxf(m, fabsf(xr[c]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // exponent-only scale: s = 2^(14 - floor(log2 m)); m == 0, inf or nan -> s = 1
+    float s = 1.f, is = 1.f;
+    if (m > 0.f && m < INFINITY) {
+      int e;
+      frexpf(m, &e);                 // m = f * 2^e, f in [0.5, 1)  ->  floor(log2 m) = e - 1
+      const int sh = min(max(15 - e, -100), 100);
+      s = ldexpf(1.f, sh); is = ldexpf(1.f, -sh);
+    }
+    if (lane == 0) inv_scale[r] = is;
+    __half* hr = hi + r * ld_out;
+    __half* lr = lo + r * ld_out;
+    for (int c = lane * 4; c < ld_out; c += 128) {
+      float v[4];
+      if (vec_ok && c + 3 < k) {
+        const float4 t = *reinterpret_cast<const float4*>(xr + c);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (c + i < k) ? xr[c + i] : 0.f;
+      }
+      __half h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xs = v[i] * s;                       // exact (power of two)
+        h[i] = __float2half_rn(xs);
+        l[i] = __float2half_rn(xs - __half2float(h[i]));  // the difference is exact in fp32
+      }
+      *reinterpret_cast<uint2*>(hr + c) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(lr + c) = *reinterpret_cast<const uint2*>(l);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -274,19 +350,19 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp32 row-major (rows, k) matrix with row stride ld; box = (bk, box_rows); OOB reads give zeros.
-static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int k, int64_t ld, int bk, int box_rows) {
+static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int k, int64_t ld, int bk, int box_rows, int elem) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return LCREC_ERR_CUDA; }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 3)) {
-    set_error("TMA operand must be 16-byte aligned with a row stride multiple of 4 floats");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem) & 15)) {
+    set_error("TMA operand must be 16-byte aligned with a row stride multiple of 16 bytes");
     return LCREC_ERR_ARG;
   }
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
   cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = bk * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+  CUtensorMapSwizzle sw = bk * elem == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(m, elem == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld k %d ld %lld)", (int)r, (long long)rows, k, (long long)ld); return LCREC_ERR_CUDA; }
@@ -294,49 +370,66 @@ static int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int k, int64
 }
 
 struct LinearProblem {
-  const float *a_hi, *a_lo; int64_t n_rows; int k; int64_t lda;
-  const float *w_hi, *w_lo; int n_out; int64_t ldw;
+  const void *a_hi, *a_lo; int64_t n_rows; int k; int64_t lda;     // fp32 (tf32 engine) or __half (f16 engine)
+  const void *w_hi, *w_lo; int n_out; int64_t ldw;
+  bool f16 = false; const float* row_scale = nullptr; const float* col_scale = nullptr;
   const float* bias; int relu;
   float* y; int64_t ldy; float *y_hi, *y_lo; int64_t ld_split;
   int acc_chunk;   // K elements per TMEM chunk, 0 = all
   int variant;     // 0 = default tile choice; 1 = force BK=32 two-stage for BN=256
 };
 
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, bool F16 = false>
 static int launch_cfg(const LinearProblem& p, cudaStream_t st) {
-  using C = LinearCfg<BN, BK, STAGES>;
+  using C = LinearCfg<BN, BK, STAGES, F16>;
   static bool attr_set = false;
-  auto kern = linear_tf32x3_kernel<BN, BK, STAGES>;
+  auto kern = linear_split3_kernel<BN, BK, STAGES, F16>;
   if (!attr_set) {
     LC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  LC_TRY(make_map(&ma_hi, p.a_hi, p.n_rows, p.k, p.lda, BK, kTileM));
-  LC_TRY(make_map(&ma_lo, p.a_lo, p.n_rows, p.k, p.lda, BK, kTileM));
-  LC_TRY(make_map(&mb_hi, p.w_hi, p.n_out, p.k, p.ldw, BK, BN));
-  LC_TRY(make_map(&mb_lo, p.w_lo, p.n_out, p.k, p.ldw, BK, BN));
+  LC_TRY(make_map(&ma_hi, p.a_hi, p.n_rows, p.k, p.lda, BK, kTileM, C::ELEM));
+  LC_TRY(make_map(&ma_lo, p.a_lo, p.n_rows, p.k, p.lda, BK, kTileM, C::ELEM));
+  LC_TRY(make_map(&mb_hi, p.w_hi, p.n_out, p.k, p.ldw, BK, BN, C::ELEM));
+  LC_TRY(make_map(&mb_lo, p.w_lo, p.n_out, p.k, p.ldw, BK, BN, C::ELEM));
   LinearArgs a;
   a.n_rows = p.n_rows; a.n_out = p.n_out;
   a.num_kblocks = (int)ceil_div(p.k, BK);
   a.chunk_kblocks = p.acc_chunk <= 0 ? a.num_kblocks : (int)std::max<int64_t>(1, p.acc_chunk / BK);
   a.relu = p.relu; a.bias = p.bias; a.y = p.y; a.ldy = p.ldy; a.y_hi = p.y_hi; a.y_lo = p.y_lo; a.ld_split = p.ld_split;
+  a.row_scale = p.row_scale; a.col_scale = p.col_scale;
   const int tiles_n = (int)ceil_div(p.n_out, BN);
   const int64_t tiles_m = ceil_div(p.n_rows, kTileM);
   const int64_t grid = tiles_m * tiles_n;
   if (grid <= 0 || grid > 0x7fffffffLL) { set_error("linear: grid %lld out of range", (long long)grid); return LCREC_ERR_ARG; }
   kern<<<(unsigned)grid, kThreads, C::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a, tiles_n);
-  LC_LAUNCH_CHECK("linear_tf32x3_kernel");
+  LC_LAUNCH_CHECK("linear_split3_kernel");
   return LCREC_OK;
 }
 
 int launch_linear(const LinearProblem& p, cudaStream_t st) {
   if (p.n_rows == 0) return LCREC_OK;
   if (p.k <= 0 || p.n_out <= 0) { set_error("linear: empty K or N"); return LCREC_ERR_ARG; }
+  if (p.f16) {   // same stage bytes as the tf32 configurations, twice the K per block
+    if (p.n_out > 128) return p.variant == 1 ? launch_cfg<256, 64, 2, true>(p, st) : launch_cfg<256, 32, 4, true>(p, st);
+    if (p.n_out > 64) return launch_cfg<128, 64, 3, true>(p, st);
+    if (p.n_out > 32) return launch_cfg<64, 64, 4, true>(p, st);
+    return launch_cfg<32, 64, 4, true>(p, st);
+  }
   if (p.n_out > 128) return p.variant == 1 ? launch_cfg<256, 32, 2>(p, st) : launch_cfg<256, 16, 4>(p, st);
   if (p.n_out > 64) return launch_cfg<128, 32, 3>(p, st);
   if (p.n_out > 32) return launch_cfg<64, 32, 4>(p, st);
   return launch_cfg<32, 32, 4>(p, st);
+}
+
+int launch_split_f16(const float* x, int64_t rows, int k, int64_t ldx, __half* hi, __half* lo, int64_t ld_out,
+                     float* inv_scale, cudaStream_t st) {
+  if (rows == 0) return LCREC_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(rows, 8), (int64_t)num_sms() * 16);
+  split_f16_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, rows, k, ldx, hi, lo, ld_out, inv_scale);
+  LC_LAUNCH_CHECK("split_f16_rows_kernel");
+  return LCREC_OK;
 }
 
 int launch_split(const float* x, int64_t rows, int k, int64_t ldx, float* hi, float* lo, int64_t ld_out,
@@ -358,15 +451,20 @@ using namespace lcrec;
 struct lcrec_mlp {
   int n_layers = 0;
   std::vector<int> dims;
-  std::vector<float*> w_hi, w_lo, bias;   // device, owned
+  std::vector<float*> w_hi, w_lo, bias;   // tf32 engine: device, owned
   std::vector<int64_t> ldw;
+  std::vector<__half*> h_hi, h_lo;        // f16 engine: split weights + 1/s per output channel
+  std::vector<float*> h_scale;
+  std::vector<int64_t> ldh;
   int relu_last = 0;
   int acc_chunk = 64;   // fp32-SIMT-level accumulation error (measured: 4.8e-7 vs cuBLAS sgemm 1.0e-6 at K=4096)
   int variant = 0;
-  int max_hidden_ld = 0;
+  int engine = 0;       // 0 = tf32 x3, 1 = f16 x3
+  int max_hidden = 0;
 };
 
 static inline int64_t ld4(int64_t k) { return round_up(k, 4); }
+static inline int64_t ld8(int64_t k) { return round_up(k, 8); }
 
 extern "C" int lcrec_mlp_update(lcrec_mlp_t* m, const float* const* weights, const float* const* biases,
                                 void* stream) {
@@ -375,6 +473,8 @@ extern "C" int lcrec_mlp_update(lcrec_mlp_t* m, const float* const* weights, con
   for (int l = 0; l < m->n_layers; ++l) {
     LC_ARG(weights[l] != nullptr);
     LC_TRY(launch_split(weights[l], m->dims[l + 1], m->dims[l], m->dims[l], m->w_hi[l], m->w_lo[l], m->ldw[l], st));
+    LC_TRY(launch_split_f16(weights[l], m->dims[l + 1], m->dims[l], m->dims[l], m->h_hi[l], m->h_lo[l], m->ldh[l],
+                            m->h_scale[l], st));
     if (biases && biases[l]) {
       LC_CUDA(cudaMemcpyAsync(m->bias[l], biases[l], sizeof(float) * m->dims[l + 1], cudaMemcpyDeviceToDevice, st));
     } else {
@@ -394,14 +494,18 @@ extern "C" int lcrec_mlp_create(int n_layers, const int32_t* dims, const float* 
   m->relu_last = relu_last;
   for (int l = 0; l <= n_layers; ++l) {
     if (dims[l] <= 0) { delete m; set_error("mlp: non-positive dimension"); return LCREC_ERR_ARG; }
-    if (l > 0 && l < n_layers) m->max_hidden_ld = std::max<int>(m->max_hidden_ld, (int)ld4(dims[l]));
+    if (l > 0 && l < n_layers) m->max_hidden = std::max<int>(m->max_hidden, dims[l]);
   }
   m->w_hi.assign(n_layers, nullptr); m->w_lo.assign(n_layers, nullptr); m->bias.assign(n_layers, nullptr);
-  m->ldw.assign(n_layers, 0);
+  m->h_hi.assign(n_layers, nullptr); m->h_lo.assign(n_layers, nullptr); m->h_scale.assign(n_layers, nullptr);
+  m->ldw.assign(n_layers, 0); m->ldh.assign(n_layers, 0);
   for (int l = 0; l < n_layers; ++l) {
-    m->ldw[l] = ld4(dims[l]);
+    m->ldw[l] = ld4(dims[l]); m->ldh[l] = ld8(dims[l]);
     const size_t wbytes = sizeof(float) * (size_t)dims[l + 1] * m->ldw[l];
+    const size_t hbytes = sizeof(__half) * (size_t)dims[l + 1] * m->ldh[l];
     if (cudaMalloc(&m->w_hi[l], wbytes) != cudaSuccess || cudaMalloc(&m->w_lo[l], wbytes) != cudaSuccess ||
+        cudaMalloc(&m->h_hi[l], hbytes) != cudaSuccess || cudaMalloc(&m->h_lo[l], hbytes) != cudaSuccess ||
+        cudaMalloc(&m->h_scale[l], sizeof(float) * dims[l + 1]) != cudaSuccess ||
         cudaMalloc(&m->bias[l], sizeof(float) * dims[l + 1]) != cudaSuccess) {
       set_error("mlp: cudaMalloc of split weights failed: %s", cudaGetErrorString(cudaGetLastError()));
       lcrec_mlp_destroy(m);
@@ -419,6 +523,9 @@ extern "C" int lcrec_mlp_destroy(lcrec_mlp_t* m) {
   for (auto p : m->w_hi) if (p) cudaFree(p);
   for (auto p : m->w_lo) if (p) cudaFree(p);
   for (auto p : m->bias) if (p) cudaFree(p);
+  for (auto p : m->h_hi) if (p) cudaFree(p);
+  for (auto p : m->h_lo) if (p) cudaFree(p);
+  for (auto p : m->h_scale) if (p) cudaFree(p);
   delete m;
   return LCREC_OK;
 }
@@ -435,14 +542,66 @@ extern "C" int lcrec_mlp_set_variant(lcrec_mlp_t* m, int variant) {
   return LCREC_OK;
 }
 
+extern "C" int lcrec_mlp_set_engine(lcrec_mlp_t* m, int engine) {
+  LC_ARG(m != nullptr && (engine == 0 || engine == 1));
+  m->engine = engine;
+  return LCREC_OK;
+}
+
 extern "C" int lcrec_mlp_in_dim(const lcrec_mlp_t* m) { return m ? m->dims.front() : -1; }
 extern "C" int lcrec_mlp_out_dim(const lcrec_mlp_t* m) { return m ? m->dims.back() : -1; }
 
 extern "C" int64_t lcrec_mlp_workspace_bytes(const lcrec_mlp_t* m, int64_t n_rows) {
   if (!m || n_rows < 0) return -1;
-  int64_t b = 2 * arena_need(sizeof(float) * n_rows * ld4(m->dims[0]));          // split input
-  b += 4 * arena_need(sizeof(float) * n_rows * std::max(m->max_hidden_ld, 4));  // hi/lo ping-pong
-  return b + 1024;
+  const int64_t hid = std::max(m->max_hidden, 8);
+  // tf32 engine: split input (2 fp32) + hi/lo ping-pong (4 fp32 hidden); f16 engine: split input (2 fp16) +
+  // split hidden (2 fp16) + one fp32 hidden + row scales.  Sized for the larger of the two.
+  const int64_t tf = 2 * arena_need(sizeof(float) * n_rows * ld4(m->dims[0])) + 4 * arena_need(sizeof(float) * n_rows * ld4(hid));
+  const int64_t hf = 2 * arena_need(sizeof(__half) * n_rows * ld8(m->dims[0])) + 2 * arena_need(sizeof(__half) * n_rows * ld8(hid)) +
+                     arena_need(sizeof(float) * n_rows * ld4(hid)) + arena_need(sizeof(float) * n_rows);
+  return std::max(tf, hf) + 1024;
+}
+
+static int mlp_forward_f16(lcrec_mlp_t* m, const float* x, int64_t n_rows, float* y, float* const* acts, void* workspace,
+                           int64_t workspace_bytes, cudaStream_t st) {
+  Arena ar(workspace, workspace_bytes);
+  const int64_t ld0 = ld8(m->dims[0]);
+  const int64_t hid = std::max(m->max_hidden, 8);
+  __half* in_hi = ar.take<__half>(n_rows * ld0);
+  __half* in_lo = ar.take<__half>(n_rows * ld0);
+  __half* hid_hi = ar.take<__half>(n_rows * ld8(hid));
+  __half* hid_lo = ar.take<__half>(n_rows * ld8(hid));
+  float* ybuf = ar.take<float>(n_rows * ld4(hid));
+  float* rscale = ar.take<float>(n_rows);
+  if (!ar.ok()) { set_error("mlp_forward: workspace too small (%lld bytes given, %lld needed)", (long long)workspace_bytes, (long long)lcrec_mlp_workspace_bytes(m, n_rows)); return LCREC_ERR_NOMEM; }
+  { ProfScope prof(0, st); LC_TRY(launch_split_f16(x, n_rows, m->dims[0], m->dims[0], in_hi, in_lo, ld0, rscale, st)); }
+  const __half *a_hi = in_hi, *a_lo = in_lo;
+  int64_t lda = ld0;
+  for (int l = 0; l < m->n_layers; ++l) {
+    const bool last = (l == m->n_layers - 1);
+    LinearProblem p{};
+    p.f16 = true; p.row_scale = rscale; p.col_scale = m->h_scale[l];
+    p.a_hi = a_hi; p.a_lo = a_lo; p.n_rows = n_rows; p.k = m->dims[l]; p.lda = lda;
+    p.w_hi = m->h_hi[l]; p.w_lo = m->h_lo[l]; p.n_out = m->dims[l + 1]; p.ldw = m->ldh[l];
+    p.bias = m->bias[l]; p.relu = last ? m->relu_last : 1;
+    p.acc_chunk = m->acc_chunk; p.variant = m->variant;
+    float* out = last ? y : ((acts && acts[l]) ? acts[l] : ybuf);
+    const int64_t ldo = last ? m->dims[l + 1] : ((acts && acts[l]) ? m->dims[l + 1] : ld4(m->dims[l + 1]));
+    p.y = out; p.ldy = ldo;
+    if ((p.ldy & 3) || (reinterpret_cast<uintptr_t>(p.y) & 15)) {
+      set_error("mlp_forward: output width %lld must be a multiple of 4 floats and 16-byte aligned", (long long)p.ldy);
+      return LCREC_ERR_UNSUPPORTED;
+    }
+    { ProfScope prof(1 + std::min(l, 15), st); LC_TRY(launch_linear(p, st)); }
+    if (!last) {
+      ProfScope prof(17, st);
+      LC_TRY(launch_split_f16(out, n_rows, m->dims[l + 1], ldo, hid_hi, hid_lo, ld8(m->dims[l + 1]), rscale, st));
+      a_hi = hid_hi; a_lo = hid_lo; lda = ld8(m->dims[l + 1]);
+    }
+  }
+  if (acts && acts[m->n_layers - 1] && acts[m->n_layers - 1] != y)
+    LC_CUDA(cudaMemcpyAsync(acts[m->n_layers - 1], y, sizeof(float) * n_rows * m->dims[m->n_layers], cudaMemcpyDeviceToDevice, st));
+  return LCREC_OK;
 }
 
 extern "C" int lcrec_mlp_forward(lcrec_mlp_t* m, const float* x, int64_t n_rows, float* y, float* const* acts,
@@ -451,11 +610,12 @@ extern "C" int lcrec_mlp_forward(lcrec_mlp_t* m, const float* x, int64_t n_rows,
   if (n_rows == 0) return LCREC_OK;
   LC_ARG(x != nullptr && y != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->engine == 1) return mlp_forward_f16(m, x, n_rows, y, acts, workspace, workspace_bytes, st);
   Arena ar(workspace, workspace_bytes);
   const int64_t ld0 = ld4(m->dims[0]);
   float* in_hi = ar.take<float>(n_rows * ld0);
   float* in_lo = ar.take<float>(n_rows * ld0);
-  const int64_t hld = std::max(m->max_hidden_ld, 4);
+  const int64_t hld = ld4(std::max(m->max_hidden, 8));
   float* buf[2][2];
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) buf[i][j] = ar.take<float>(n_rows * hld);
   if (!ar.ok()) { set_error("mlp_forward: workspace too small (%lld bytes given, %lld needed)", (long long)workspace_bytes, (long long)lcrec_mlp_workspace_bytes(m, n_rows)); return LCREC_ERR_NOMEM; }
@@ -487,8 +647,10 @@ extern "C" int lcrec_mlp_forward(lcrec_mlp_t* m, const float* x, int64_t n_rows,
 }
 
 // Single fused Linear(+bias)(+ReLU) on raw fp32 operands (splits both on the fly into `ws`).
+// variant: bit 0 = alternative tile for wide N, bit 1 = f16 x3 engine instead of tf32 x3.
 extern "C" int64_t lcrec_linear_workspace_bytes(int64_t n_rows, int k_in, int n_out) {
-  return 2 * arena_need(sizeof(float) * n_rows * ld4(k_in)) + 2 * arena_need(sizeof(float) * (int64_t)n_out * ld4(k_in)) + 1024;
+  return 2 * arena_need(sizeof(float) * n_rows * ld4(k_in)) + 2 * arena_need(sizeof(float) * (int64_t)n_out * ld4(k_in)) +
+         arena_need(sizeof(float) * n_rows) + arena_need(sizeof(float) * n_out) + 1024;
 }
 extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* w, const float* b,
                                     int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,
@@ -500,15 +662,27 @@ extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, co
   LC_ARG((n_out & 3) == 0);
   cudaStream_t st = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
+  LinearProblem p{};
+  p.n_rows = n_rows; p.k = k_in; p.n_out = n_out; p.bias = b; p.relu = relu;
+  p.y = y; p.ldy = n_out; p.acc_chunk = acc_chunk; p.variant = variant & 1;
+  if (variant & 2) {
+    const int64_t ldk = ld8(k_in);
+    __half* a_hi = ar.take<__half>(n_rows * ldk); __half* a_lo = ar.take<__half>(n_rows * ldk);
+    __half* w_hi = ar.take<__half>((int64_t)n_out * ldk); __half* w_lo = ar.take<__half>((int64_t)n_out * ldk);
+    float* rs = ar.take<float>(n_rows); float* cs = ar.take<float>(n_out);
+    if (!ar.ok()) { set_error("linear_forward: workspace too small"); return LCREC_ERR_NOMEM; }
+    LC_TRY(launch_split_f16(x, n_rows, k_in, k_in, a_hi, a_lo, ldk, rs, st));
+    LC_TRY(launch_split_f16(w, n_out, k_in, k_in, w_hi, w_lo, ldk, cs, st));
+    p.f16 = true; p.row_scale = rs; p.col_scale = cs;
+    p.a_hi = a_hi; p.a_lo = a_lo; p.lda = ldk; p.w_hi = w_hi; p.w_lo = w_lo; p.ldw = ldk;
+    return launch_linear(p, st);
+  }
   const int64_t ldk = ld4(k_in);
   float* a_hi = ar.take<float>(n_rows * ldk); float* a_lo = ar.take<float>(n_rows * ldk);
   float* w_hi = ar.take<float>((int64_t)n_out * ldk); float* w_lo = ar.take<float>((int64_t)n_out * ldk);
   if (!ar.ok()) { set_error("linear_forward: workspace too small"); return LCREC_ERR_NOMEM; }
   LC_TRY(launch_split(x, n_rows, k_in, k_in, a_hi, a_lo, ldk, st));
   LC_TRY(launch_split(w, n_out, k_in, k_in, w_hi, w_lo, ldk, st));
-  LinearProblem p{};
-  p.a_hi = a_hi; p.a_lo = a_lo; p.n_rows = n_rows; p.k = k_in; p.lda = ldk;
-  p.w_hi = w_hi; p.w_lo = w_lo; p.n_out = n_out; p.ldw = ldk; p.bias = b; p.relu = relu;
-  p.y = y; p.ldy = n_out; p.acc_chunk = acc_chunk; p.variant = variant;
+  p.a_hi = a_hi; p.a_lo = a_lo; p.lda = ldk; p.w_hi = w_hi; p.w_lo = w_lo; p.ldw = ldk;
   return launch_linear(p, st);
 }

@@ -33,6 +33,18 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+import os as _os
+
+# GEMM operand encoding used by every MlpHandle created afterwards: 1 = f16 x3 (default), 0 = tf32 x3.
+DEFAULT_ENGINE = int(_os.environ.get("LCREC_ENGINE", "1"))
+
+
+def set_default_engine(engine: int) -> None:
+    global DEFAULT_ENGINE
+    assert engine in (0, 1)
+    DEFAULT_ENGINE = int(engine)
+
+
 def launch_count() -> int:
     return int(_lib.load().lcrec_launch_count())
 
@@ -72,6 +84,7 @@ class MlpHandle:
             _lib.check(self.lib.lcrec_mlp_create(self.n_layers, _lib.i32_array(self.dims), ws, bs, int(relu_last),
                                                  _stream(weights[0]), C.byref(self.handle)))
         self._workspace: Optional[torch.Tensor] = None
+        self.set_engine(DEFAULT_ENGINE)
 
     def _pack(self, weights, biases):
         self._keep = [_f32c(w) for w in weights]
@@ -88,6 +101,10 @@ class MlpHandle:
 
     def set_acc_chunk(self, k_elems: int) -> None:
         _lib.check(self.lib.lcrec_mlp_set_acc_chunk(self.handle, int(k_elems)))
+
+    def set_engine(self, engine: int) -> None:
+        """0 = tf32 x3, 1 = f16 x3 (see include/lcrec_b200.h)."""
+        _lib.check(self.lib.lcrec_mlp_set_engine(self.handle, int(engine)))
 
     def set_variant(self, v: int) -> None:
         _lib.check(self.lib.lcrec_mlp_set_variant(self.handle, int(v)))
@@ -121,8 +138,11 @@ class MlpHandle:
 
 
 def linear_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool,
-                   acc_chunk: int = 64, variant: int = 0) -> torch.Tensor:
-    """relu?(x @ w.T + b) with the 3xTF32 tcgen05 kernel (nn.Linear, layers.py:23)."""
+                   acc_chunk: int = 64, variant: Optional[int] = None) -> torch.Tensor:
+    """relu?(x @ w.T + b) with the split-operand tcgen05 kernel (nn.Linear, layers.py:23).
+    variant: bit 0 = alternative tile, bit 1 = f16 x3 engine (default: the module-wide DEFAULT_ENGINE)."""
+    if variant is None:
+        variant = 2 * DEFAULT_ENGINE
     _need_cuda(x, w)
     lib = _lib.load()
     x2, w2 = _f32c(x.reshape(-1, w.shape[1])), _f32c(w)

@@ -49,7 +49,7 @@ def test_linear_matches_fp64(n, k, m, relu):
     ref = x.double() @ w.double().t() + b.double()
     if relu:
         ref = ref.clamp_min(0)
-    for variant in (0, 1):
+    for variant in (0, 1, 2, 3):      # tile variant x operand encoding (tf32 x3 / f16 x3)
         y = ops.linear_forward(x, w, b, relu, variant=variant)
         scale = (x.double().abs() @ w.double().abs().t()).mean().item() + 1e-30
         err = (y.double() - ref).abs().max().item() / scale
