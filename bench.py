@@ -225,6 +225,8 @@ def run_gpu_arm(a):
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
     if world > 1:
+        # NCCL's version / debug lines go to stdout; keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "lcrec_nccl_%h_%p.log"))
         dist.init_process_group("nccl", device_id=device)
     pk = peaks()
     ops.set_default_engine(a.engine)

@@ -5,12 +5,14 @@ The reference's index/ directory is single-process; this is the north-star shard
 
 * PASS 0 shards naturally - contiguous item blocks per rank, encoder weights and codebooks
   replicated, no communication (the 16 KB/item embeddings never leave their rank);
-* collision detection needs the global code table: after PASS 0 the packed codes (32 B/item) and
-  the residuals entering the last level (128 B/item) are all-gathered ONCE;
-* every round each rank derives the same CSR of collision groups from the same table
-  (deterministic sort), resolves the groups ``g % world == rank`` with the per-group Sinkhorn
-  kernel, and the last-level code deltas are summed with one all-reduce (8 B/item).  Groups are
-  disjoint, so the result is identical to the single-GPU run bit for bit.
+* collision detection needs a global view, but two items can only ever collide if they share the
+  first L-1 codes (the rounds rewrite the LAST level only, generate_indices.py:101-105), so the
+  global problem splits into independent PREFIX BUCKETS.  After PASS 0 the codes (32 B/item) and
+  the residuals entering the last level (128 B/item) are all-gathered once; rank r then owns the
+  buckets with ``prefix % world == r``, runs the whole <=20-round loop on them locally (1/world of
+  the sort and Sinkhorn work, no per-round communication), and one all-reduce of the last-level
+  codes (8 B/item) returns the results.  Groups, member order and arithmetic are exactly those of
+  the single-GPU run, so the result is identical bit for bit.
 
 The arithmetic lives behind a small backend interface so that the host logic above can be
 exercised with ``gloo`` on CPU in the tests (where the backend is the numpy oracle); the product
@@ -84,50 +86,75 @@ class CudaBackend:
         self.indexer.pass0(x_local, 0)
         return self.indexer.codes_view(n).clone(), self.indexer.resid_view(n).clone()
 
-    def collisions(self, codes_all: torch.Tensor) -> dict:
-        return self.ops.collisions(codes_all, self.n_codes)
+    def collisions(self, codes: torch.Tensor) -> dict:
+        return self.ops.collisions(codes, self.n_codes)
 
-    def resolve(self, resid_all: torch.Tensor, codes_all: torch.Tensor, info: dict, mod: int, rem: int) -> None:
-        flags = self.ops.sinkhorn_groups(resid_all, self.cbs[-1], info["offsets"], info["members"],
+    def resolve(self, resid: torch.Tensor, codes: torch.Tensor, info: dict) -> None:
+        flags = self.ops.sinkhorn_groups(resid, self.cbs[-1], info["offsets"], info["members"],
                                          info["counts_dev"][1:2], info["n_groups"], info["n_rows"], self.eps,
-                                         self.iters, codes_all, codes_all.shape[1] - 1, part_mod=mod, part_rem=rem)
+                                         self.iters, codes, codes.shape[1] - 1)
         if flags & 6:
             raise RuntimeError(f"sinkhorn_groups failed with flags {flags}")
 
 
-def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank: int, max_rounds: int = 20,
-                           group=None):
-    """Sharded ``generate_indices``: returns (codes of this rank's items, stats).  Collective: every
-    rank of ``group`` must call it."""
-    codes_local, resid_local = backend.pass0(x_local)
-    if plan.world > 1:
-        codes_all = all_gather_rows(codes_local, plan, rank, group)
-        resid_all = all_gather_rows(resid_local, plan, rank, group)
-    else:
-        codes_all, resid_all = codes_local, resid_local
-    codes_all = codes_all.contiguous()
-    n = plan.n_total
-    rounds = 0
-    first = None
-    rows_total = 0
-    while True:                                               # generate_indices.py:108-128
-        info = backend.collisions(codes_all)
-        if first is None:
+def bucket_owner(codes: torch.Tensor, n_codes, world: int) -> torch.Tensor:
+    """Owner rank of every item's prefix bucket: mixed-radix value of the first L-1 codes, modulo world."""
+    prefix = torch.zeros(codes.shape[0], dtype=torch.int64, device=codes.device)
+    for l in range(codes.shape[1] - 1):
+        prefix = prefix * int(n_codes[l]) + codes[:, l]
+    return prefix % world
+
+
+def resolve_rounds(backend, codes: torch.Tensor, resid: torch.Tensor, max_rounds: int):
+    """generate_indices.py:108-128 on one self-contained set of items (codes is updated in place)."""
+    n = codes.shape[0]
+    rounds = rows_total = 0
+    first = (0, 0)
+    info = {"n_unique": n, "max_multiplicity": 1 if n else 0}
+    while n > 0:
+        info = backend.collisions(codes)
+        if rounds == 0:
             first = (info["n_groups"], info["n_rows"])
         if info["n_unique"] == n or rounds >= max_rounds:
             break
-        last = codes_all.shape[1] - 1
-        if plan.world > 1:
-            old = codes_all[:, last].clone()
-            backend.resolve(resid_all, codes_all, info, plan.world, rank)
-            delta = codes_all[:, last] - old
-            dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
-            codes_all[:, last] = old + delta
-        else:
-            backend.resolve(resid_all, codes_all, info, 1, 0)
+        backend.resolve(resid, codes, info)
         rows_total += info["n_rows"]
         rounds += 1
-    stats = {"rounds": rounds, "n_unique": info["n_unique"], "groups_round1": first[0], "rows_round1": first[1],
-             "sinkhorn_rows": rows_total, "max_multiplicity": info["max_multiplicity"],
-             "collision_rate": (n - info["n_unique"]) / max(n, 1)}
-    return codes_all[plan.slice(rank)], stats
+    return {"rounds": rounds, "n_unique": info["n_unique"], "groups_round1": first[0], "rows_round1": first[1],
+            "sinkhorn_rows": rows_total, "max_multiplicity": info["max_multiplicity"]}
+
+
+def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank: int, max_rounds: int = 20,
+                           group=None, n_codes=None):
+    """Sharded ``generate_indices``: returns (codes of this rank's items, stats).  Collective: every
+    rank of ``group`` must call it."""
+    codes_local, resid_local = backend.pass0(x_local)
+    n_codes = n_codes or getattr(backend, "n_codes")
+    if plan.world == 1:
+        codes = codes_local.contiguous()
+        stats = resolve_rounds(backend, codes, resid_local, max_rounds)
+        stats["collision_rate"] = (plan.n_total - stats["n_unique"]) / max(plan.n_total, 1)
+        return codes, stats
+    codes_all = all_gather_rows(codes_local, plan, rank, group)
+    resid_all = all_gather_rows(resid_local, plan, rank, group)
+    mine = torch.nonzero(bucket_owner(codes_all, n_codes, plan.world) == rank).squeeze(1)   # ascending item ids
+    sub_codes = codes_all.index_select(0, mine).contiguous()
+    sub_resid = resid_all.index_select(0, mine).contiguous()
+    st = resolve_rounds(backend, sub_codes, sub_resid, max_rounds)
+    last = codes_all.shape[1] - 1
+    final_last = torch.zeros(plan.n_total, dtype=torch.int64, device=codes_all.device)
+    final_last[mine] = sub_codes[:, last]
+    agg = torch.tensor([st["n_unique"], st["groups_round1"], st["rows_round1"], st["sinkhorn_rows"]], dtype=torch.int64,
+                       device=codes_all.device)
+    mx = torch.tensor([st["rounds"], st["max_multiplicity"]], dtype=torch.int64, device=codes_all.device)
+    dist.all_reduce(final_last, op=dist.ReduceOp.SUM, group=group)       # buckets are disjoint: a sum is a scatter
+    dist.all_reduce(agg, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    out = codes_local.clone()
+    out[:, last] = final_last[plan.slice(rank)]
+    n_unique, g1, r1, rows = [int(v) for v in agg.tolist()]
+    rounds, max_mult = [int(v) for v in mx.tolist()]
+    stats = {"rounds": rounds, "n_unique": n_unique, "groups_round1": g1, "rows_round1": r1, "sinkhorn_rows": rows,
+             "max_multiplicity": max_mult, "collision_rate": (plan.n_total - n_unique) / max(plan.n_total, 1),
+             "bucket_items_this_rank": int(mine.numel())}
+    return out, stats

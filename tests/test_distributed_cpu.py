@@ -1,6 +1,6 @@
 """world_size-2 gloo test of the sharded generation host logic (lcrec_b200.distributed) on CPU.
 The per-rank arithmetic is supplied by an oracle-backed stand-in backend (tests only); what is under
-test is the shard plan, the ragged all-gather, the group partition and the delta all-reduce."""
+test is the shard plan, the ragged all-gather, the prefix-bucket ownership and the final all-reduce."""
 import os
 import socket
 
@@ -25,17 +25,18 @@ class OracleBackend:
         resids, _, codes = O.rq_trace(z, self.p)
         return torch.from_numpy(codes), torch.from_numpy(resids[-1])
 
-    def collisions(self, codes_all):
-        c = codes_all.numpy()
-        groups = sorted(O.collision_groups(c), key=lambda g: tuple(c[g[0]]))
+    n_codes = [32, 32, 32, 32]
+
+    def collisions(self, codes):
+        c = codes.numpy()
+        groups = O.collision_groups(c)
         return {"groups": groups, "n_groups": len(groups), "n_rows": sum(map(len, groups)), "n_unique": O.n_unique_codes(c),
                 "max_multiplicity": O.max_conflicts(c)}
 
-    def resolve(self, resid_all, codes_all, info, mod, rem):
-        r = resid_all.numpy()
-        for gi, g in enumerate(info["groups"]):
-            if gi % mod == rem:
-                codes_all[g, -1] = torch.from_numpy(O.vq_assign(r[g], self.p.codebooks[-1], True, self.p_sk.sk_epsilons[-1], self.p.sk_iters))
+    def resolve(self, resid, codes, info):
+        r = resid.numpy()
+        for g in info["groups"]:
+            codes[g, -1] = torch.from_numpy(O.vq_assign(r[g], self.p.codebooks[-1], True, self.p_sk.sk_epsilons[-1], self.p.sk_iters))
 
 
 def _load():
@@ -64,6 +65,14 @@ def test_shard_plan():
     assert [plan.count(r) for r in range(4)] == [3, 3, 2, 2]
     assert [plan.start(r) for r in range(4)] == [0, 3, 6, 8] and plan.max_count == 3
     assert ShardPlan(8, 8).slice(7) == slice(7, 8)
+
+
+def test_bucket_owner_keeps_collision_candidates_together():
+    from lcrec_b200.distributed import bucket_owner
+    codes = torch.tensor([[1, 2, 3, 9], [1, 2, 3, 4], [0, 0, 1, 4], [31, 31, 31, 0]])
+    own = bucket_owner(codes, [32] * 4, 3)
+    assert own[0] == own[1]                       # same prefix -> same owner, whatever the last code
+    assert own.tolist() == [((1 * 32 + 2) * 32 + 3) % 3] * 2 + [1 % 3, ((31 * 32 + 31) * 32 + 31) % 3]
 
 
 def test_two_rank_generation_equals_single_process(tmp_path):
