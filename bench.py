@@ -225,9 +225,19 @@ def run_gpu_arm(a):
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
     if world > 1:
-        # NCCL's version / debug lines go to stdout; keep stdout to the single JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "lcrec_nccl_%h_%p.log"))
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner / debug lines on stdout while the communicator is created: point fd 1
+        # at stderr for that moment so that stdout carries nothing but the single JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     pk = peaks()
     ops.set_default_engine(a.engine)
     ws, bs, cbs, head = make_model()

@@ -98,11 +98,13 @@ class CudaBackend:
 
 
 def bucket_owner(codes: torch.Tensor, n_codes, world: int) -> torch.Tensor:
-    """Owner rank of every item's prefix bucket: mixed-radix value of the first L-1 codes, modulo world."""
+    """Owner rank of every item's prefix bucket: the mixed-radix value of the first L-1 codes, mixed with a
+    multiplicative hash (so that skewed code usage still spreads evenly), modulo world."""
     prefix = torch.zeros(codes.shape[0], dtype=torch.int64, device=codes.device)
     for l in range(codes.shape[1] - 1):
         prefix = prefix * int(n_codes[l]) + codes[:, l]
-    return prefix % world
+    mixed = (prefix * 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF) >> 24      # wraps mod 2^64, then the high bits
+    return mixed % world
 
 
 def resolve_rounds(backend, codes: torch.Tensor, resid: torch.Tensor, max_rounds: int):

@@ -72,7 +72,11 @@ def test_bucket_owner_keeps_collision_candidates_together():
     codes = torch.tensor([[1, 2, 3, 9], [1, 2, 3, 4], [0, 0, 1, 4], [31, 31, 31, 0]])
     own = bucket_owner(codes, [32] * 4, 3)
     assert own[0] == own[1]                       # same prefix -> same owner, whatever the last code
-    assert own.tolist() == [((1 * 32 + 2) * 32 + 3) % 3] * 2 + [1 % 3, ((31 * 32 + 31) * 32 + 31) % 3]
+    assert 0 <= int(own.min()) and int(own.max()) < 3
+    many = torch.randint(0, 32, (20000, 4))
+    many[:, 2] = many[:, 2] // 8 * 8                      # skewed usage of one level must still balance
+    cnt = torch.bincount(bucket_owner(many, [32] * 4, 8), minlength=8).float()
+    assert cnt.min() / cnt.max() > 0.8
 
 
 def test_two_rank_generation_equals_single_process(tmp_path):
