@@ -56,8 +56,13 @@ int lcrec_mlp_forward(lcrec_mlp_t* mlp, const float* x, int64_t n_rows, float* y
 /* accumulation chunk: number of K elements accumulated inside TMEM before the partial sum is
  * folded into fp32 registers with round-to-nearest (0 = whole K in TMEM). */
 int lcrec_mlp_set_acc_chunk(lcrec_mlp_t* mlp, int k_elems);
-/* tile variant for experiments: 0 = default (N tile 256: K block 16 x 4 stages), 1 = K block 32 x 2 stages */
+/* kernel selection / measurement switches (bit mask): 1 = alternative stage shape of the single-CTA kernel,
+ * 4 = no TMA loads after the first ring fill, 8 = no MMAs (4 and 8: timing experiments, results are garbage),
+ * 16 = never use the CTA-pair kernel, 32 = CTA-pair kernel with 6 x 32 KB stages instead of 3 x 64 KB. */
 int lcrec_mlp_set_variant(lcrec_mlp_t* mlp, int variant);
+/* measurement only: device buffer of 6 x 512 x 4 int64 that receives clock64 stamps of the pipeline roles of
+ * one CTA of the layer-0 pair kernel (producer / MMA k-blocks / MMA chunks / fold), or NULL to switch off. */
+int lcrec_mlp_set_trace(lcrec_mlp_t* mlp, void* trace);
 /* operand encoding of the GEMMs: 0 = tf32 x3 (fp32 operands split into two tf32 numbers), 1 = f16 x3 (per-row
  * power-of-two scale, two fp16 numbers; same 22-bit operand precision, twice the tensor rate). */
 int lcrec_mlp_set_engine(lcrec_mlp_t* mlp, int engine);

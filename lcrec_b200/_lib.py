@@ -30,6 +30,7 @@ SIGNATURES = {
     "lcrec_mlp_set_acc_chunk": (C.c_int, [vp, C.c_int]),
     "lcrec_mlp_set_variant": (C.c_int, [vp, C.c_int]),
     "lcrec_mlp_set_engine": (C.c_int, [vp, C.c_int]),
+    "lcrec_mlp_set_trace": (C.c_int, [vp, vp]),
     "lcrec_mlp_in_dim": (C.c_int, [vp]),
     "lcrec_mlp_out_dim": (C.c_int, [vp]),
     "lcrec_linear_workspace_bytes": (i64, [i64, C.c_int, C.c_int]),

@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "linear.cuh"
 #include "sm100_ptx.cuh"
 
 namespace lcrec {
@@ -52,6 +53,7 @@ struct LinearArgs {
   int64_t ld_split;
   const float* row_scale;   // f16 engine: 1 / s_row (n_rows) and 1 / s_col (n_out); null = 1
   const float* col_scale;
+  int debug;          // measurement only: bit 0 = no TMA loads after the first ring fill, bit 1 = no MMAs (results are garbage)
 };
 
 constexpr int kTileM = 128;
@@ -126,6 +128,7 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
+        if ((args.debug & 1) && kb >= STAGES) { mbar_arrive(full_bar(s)); continue; }
         mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
         const uint32_t dst = base + s * C::STAGE_BYTES;
         tma_load_2d(dst, &map_ahi, full_bar(s), kb * BK, row0);
@@ -157,6 +160,7 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
           const uint64_t d_alo = umma_smem_desc(a_hi + C::A_BYTES, C::SBO, C::LAYOUT);
           const uint64_t d_bhi = umma_smem_desc(a_hi + 2 * C::A_BYTES, C::SBO, C::LAYOUT);
           const uint64_t d_blo = umma_smem_desc(a_hi + 2 * C::A_BYTES + C::B_BYTES, C::SBO, C::LAYOUT);
+          if (!(args.debug & 2))
 #pragma unroll
           for (int k = 0; k < BK / C::KSTEP; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);   // one MMA consumes 32 bytes along K
@@ -350,7 +354,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp32 row-major (rows, k) matrix with row stride ld; box = (bk, box_rows); OOB reads give zeros.
-static int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int k, int64_t ld, int bk, int box_rows, int elem) {
+int make_map(CUtensorMap* m, const void* ptr, int64_t rows, int k, int64_t ld, int bk, int box_rows, int elem) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return LCREC_ERR_CUDA; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem) & 15)) {
@@ -398,7 +402,7 @@ static int launch_cfg(const LinearProblem& p, cudaStream_t st) {
   a.num_kblocks = (int)ceil_div(p.k, BK);
   a.chunk_kblocks = p.acc_chunk <= 0 ? a.num_kblocks : (int)std::max<int64_t>(1, p.acc_chunk / BK);
   a.relu = p.relu; a.bias = p.bias; a.y = p.y; a.ldy = p.ldy; a.y_hi = p.y_hi; a.y_lo = p.y_lo; a.ld_split = p.ld_split;
-  a.row_scale = p.row_scale; a.col_scale = p.col_scale;
+  a.row_scale = p.row_scale; a.col_scale = p.col_scale; a.debug = (p.variant >> 2) & 3;   // variant bits 2, 3
   const int tiles_n = (int)ceil_div(p.n_out, BN);
   const int64_t tiles_m = ceil_div(p.n_rows, kTileM);
   const int64_t grid = tiles_m * tiles_n;
@@ -412,12 +416,12 @@ int launch_linear(const LinearProblem& p, cudaStream_t st) {
   if (p.n_rows == 0) return LCREC_OK;
   if (p.k <= 0 || p.n_out <= 0) { set_error("linear: empty K or N"); return LCREC_ERR_ARG; }
   if (p.f16) {   // same stage bytes as the tf32 configurations, twice the K per block
-    if (p.n_out > 128) return p.variant == 1 ? launch_cfg<256, 64, 2, true>(p, st) : launch_cfg<256, 32, 4, true>(p, st);
+    if (p.n_out > 128) return (p.variant & 1) ? launch_cfg<256, 64, 2, true>(p, st) : launch_cfg<256, 32, 4, true>(p, st);
     if (p.n_out > 64) return launch_cfg<128, 64, 3, true>(p, st);
     if (p.n_out > 32) return launch_cfg<64, 64, 4, true>(p, st);
     return launch_cfg<32, 64, 4, true>(p, st);
   }
-  if (p.n_out > 128) return p.variant == 1 ? launch_cfg<256, 32, 2>(p, st) : launch_cfg<256, 16, 4>(p, st);
+  if (p.n_out > 128) return (p.variant & 1) ? launch_cfg<256, 32, 2>(p, st) : launch_cfg<256, 16, 4>(p, st);
   if (p.n_out > 64) return launch_cfg<128, 32, 3>(p, st);
   if (p.n_out > 32) return launch_cfg<64, 32, 4>(p, st);
   return launch_cfg<32, 32, 4>(p, st);
@@ -461,6 +465,7 @@ struct lcrec_mlp {
   int variant = 0;
   int engine = 0;       // 0 = tf32 x3, 1 = f16 x3
   int max_hidden = 0;
+  void* trace = nullptr;
 };
 
 static inline int64_t ld4(int64_t k) { return round_up(k, 4); }
@@ -542,6 +547,12 @@ extern "C" int lcrec_mlp_set_variant(lcrec_mlp_t* m, int variant) {
   return LCREC_OK;
 }
 
+extern "C" int lcrec_mlp_set_trace(lcrec_mlp_t* m, void* trace) {
+  LC_ARG(m != nullptr);
+  m->trace = trace;
+  return LCREC_OK;
+}
+
 extern "C" int lcrec_mlp_set_engine(lcrec_mlp_t* m, int engine) {
   LC_ARG(m != nullptr && (engine == 0 || engine == 1));
   m->engine = engine;
@@ -551,17 +562,23 @@ extern "C" int lcrec_mlp_set_engine(lcrec_mlp_t* m, int engine) {
 extern "C" int lcrec_mlp_in_dim(const lcrec_mlp_t* m) { return m ? m->dims.front() : -1; }
 extern "C" int lcrec_mlp_out_dim(const lcrec_mlp_t* m) { return m ? m->dims.back() : -1; }
 
+static inline int64_t n_scale_groups(int64_t k) { return ceil_div(ld8(k), kPairGroup); }
+
 extern "C" int64_t lcrec_mlp_workspace_bytes(const lcrec_mlp_t* m, int64_t n_rows) {
   if (!m || n_rows < 0) return -1;
   const int64_t hid = std::max(m->max_hidden, 8);
-  // tf32 engine: split input (2 fp32) + hi/lo ping-pong (4 fp32 hidden); f16 engine: split input (2 fp16) +
-  // split hidden (2 fp16) + one fp32 hidden + row scales.  Sized for the larger of the two.
+  // tf32 engine: split input (2 fp32) + hi/lo ping-pong (4 fp32 hidden); f16 engine: split input (2 fp16) + two
+  // sets of split hidden activations (4 fp16) + one fp32 hidden + scales.  Sized for the larger of the two.
   const int64_t tf = 2 * arena_need(sizeof(float) * n_rows * ld4(m->dims[0])) + 4 * arena_need(sizeof(float) * n_rows * ld4(hid));
-  const int64_t hf = 2 * arena_need(sizeof(__half) * n_rows * ld8(m->dims[0])) + 2 * arena_need(sizeof(__half) * n_rows * ld8(hid)) +
-                     arena_need(sizeof(float) * n_rows * ld4(hid)) + arena_need(sizeof(float) * n_rows);
+  const int64_t hf = 2 * arena_need(sizeof(__half) * n_rows * ld8(m->dims[0])) + 4 * arena_need(sizeof(__half) * n_rows * ld8(hid)) +
+                     arena_need(sizeof(float) * n_rows * ld4(hid)) + arena_need(sizeof(float) * n_rows) +
+                     arena_need(sizeof(float) * n_rows * n_scale_groups(m->dims[0])) + 2 * arena_need(sizeof(float) * n_rows * n_scale_groups(hid));
   return std::max(tf, hf) + 1024;
 }
 
+// f16 x3 engine.  Wide layers (n_out a multiple of 256) run on the CTA-pair kernel with group-scaled operands and
+// hand the next wide layer its fp16 hi/lo operand straight from the epilogue; the narrow tail layers use the
+// single-CTA kernel with per-row scales (fp32 activation + split_f16_rows pass in between).
 static int mlp_forward_f16(lcrec_mlp_t* m, const float* x, int64_t n_rows, float* y, float* const* acts, void* workspace,
                            int64_t workspace_bytes, cudaStream_t st) {
   Arena ar(workspace, workspace_bytes);
@@ -569,35 +586,76 @@ static int mlp_forward_f16(lcrec_mlp_t* m, const float* x, int64_t n_rows, float
   const int64_t hid = std::max(m->max_hidden, 8);
   __half* in_hi = ar.take<__half>(n_rows * ld0);
   __half* in_lo = ar.take<__half>(n_rows * ld0);
-  __half* hid_hi = ar.take<__half>(n_rows * ld8(hid));
-  __half* hid_lo = ar.take<__half>(n_rows * ld8(hid));
+  __half* set_hi[2]; __half* set_lo[2]; float* set_scale[2];
+  for (int i = 0; i < 2; ++i) { set_hi[i] = ar.take<__half>(n_rows * ld8(hid)); set_lo[i] = ar.take<__half>(n_rows * ld8(hid)); }
   float* ybuf = ar.take<float>(n_rows * ld4(hid));
   float* rscale = ar.take<float>(n_rows);
+  float* in_scale = ar.take<float>(n_rows * n_scale_groups(m->dims[0]));
+  for (int i = 0; i < 2; ++i) set_scale[i] = ar.take<float>(n_rows * n_scale_groups(hid));
   if (!ar.ok()) { set_error("mlp_forward: workspace too small (%lld bytes given, %lld needed)", (long long)workspace_bytes, (long long)lcrec_mlp_workspace_bytes(m, n_rows)); return LCREC_ERR_NOMEM; }
-  { ProfScope prof(0, st); LC_TRY(launch_split_f16(x, n_rows, m->dims[0], m->dims[0], in_hi, in_lo, ld0, rscale, st)); }
-  const __half *a_hi = in_hi, *a_lo = in_lo;
-  int64_t lda = ld0;
+  const bool allow_pair = !(m->variant & 16);
+  auto pair_ok = [&](int l) { return allow_pair && l < m->n_layers && linear_pair_supported(m->dims[l], m->dims[l + 1], kPairGroup); };
+  // current activation: fp32 (cur, ldc) or group-scaled fp16 (grp)
+  const float* cur = x; int64_t ldc = m->dims[0];
+  SplitOperand grp{}; bool grouped = false; int next_set = 0;
   for (int l = 0; l < m->n_layers; ++l) {
     const bool last = (l == m->n_layers - 1);
+    const int k = m->dims[l], n_out = m->dims[l + 1];
+    float* act_out = (acts && acts[l]) ? acts[l] : nullptr;
+    if (pair_ok(l)) {
+      if (!grouped) {
+        ProfScope prof(l == 0 ? 0 : 17, st);
+        __half* hi = l == 0 ? in_hi : set_hi[next_set];
+        __half* lo = l == 0 ? in_lo : set_lo[next_set];
+        float* sc = l == 0 ? in_scale : set_scale[next_set];
+        if (l != 0) next_set ^= 1;
+        LC_TRY(launch_split_groups(cur, n_rows, k, ldc, hi, lo, ld8(k), sc, n_rows, st));
+        grp.hi = hi; grp.lo = lo; grp.ld = ld8(k); grp.inv_scale = sc; grp.ld_scale = n_rows; grp.group = kPairGroup;
+        grouped = true;
+      }
+      PairProblem p{};
+      p.a = grp; p.n_rows = n_rows; p.k = k;
+      p.w_hi = m->h_hi[l]; p.w_lo = m->h_lo[l]; p.ldw = m->ldh[l]; p.w_inv_scale = m->h_scale[l];
+      p.n_out = n_out; p.bias = m->bias[l]; p.relu = last ? m->relu_last : 1;
+      p.debug = ((m->variant >> 2) & 3) | ((m->variant & 32) ? 4 : 0) | ((m->variant & 64) ? 8 : 0);
+      if (l == 0) p.trace = m->trace;
+      const bool next_pair = !last && pair_ok(l + 1);
+      if (next_pair) {
+        p.o_hi = set_hi[next_set]; p.o_lo = set_lo[next_set]; p.ldo = ld8(n_out);
+        p.o_inv_scale = set_scale[next_set]; p.ld_oscale = n_rows;
+      }
+      if (last) { p.y = y; p.ldy = n_out; }
+      else if (act_out) { p.y = act_out; p.ldy = n_out; }
+      else if (!next_pair) { p.y = ybuf; p.ldy = ld4(n_out); }
+      { ProfScope prof(1 + std::min(l, 15), st); LC_TRY(launch_linear_pair(p, st)); }
+      if (next_pair) {
+        grp.hi = p.o_hi; grp.lo = p.o_lo; grp.ld = p.ldo; grp.inv_scale = p.o_inv_scale; grp.ld_scale = n_rows; grp.group = kPairGroup;
+        next_set ^= 1;
+      } else {
+        grouped = false; cur = p.y; ldc = p.ldy;
+      }
+      continue;
+    }
+    // single-CTA kernel, per-row scales
+    {
+      ProfScope prof(l == 0 ? 0 : 17, st);
+      LC_TRY(launch_split_f16(cur, n_rows, k, ldc, l == 0 ? in_hi : set_hi[0], l == 0 ? in_lo : set_lo[0], ld8(k), rscale, st));
+    }
     LinearProblem p{};
     p.f16 = true; p.row_scale = rscale; p.col_scale = m->h_scale[l];
-    p.a_hi = a_hi; p.a_lo = a_lo; p.n_rows = n_rows; p.k = m->dims[l]; p.lda = lda;
-    p.w_hi = m->h_hi[l]; p.w_lo = m->h_lo[l]; p.n_out = m->dims[l + 1]; p.ldw = m->ldh[l];
+    p.a_hi = l == 0 ? in_hi : set_hi[0]; p.a_lo = l == 0 ? in_lo : set_lo[0]; p.n_rows = n_rows; p.k = k; p.lda = ld8(k);
+    p.w_hi = m->h_hi[l]; p.w_lo = m->h_lo[l]; p.n_out = n_out; p.ldw = m->ldh[l];
     p.bias = m->bias[l]; p.relu = last ? m->relu_last : 1;
-    p.acc_chunk = m->acc_chunk; p.variant = m->variant;
-    float* out = last ? y : ((acts && acts[l]) ? acts[l] : ybuf);
-    const int64_t ldo = last ? m->dims[l + 1] : ((acts && acts[l]) ? m->dims[l + 1] : ld4(m->dims[l + 1]));
+    p.acc_chunk = m->acc_chunk; p.variant = m->variant & 15;
+    float* out = last ? y : (act_out ? act_out : ybuf);
+    const int64_t ldo = last ? n_out : (act_out ? n_out : ld4(n_out));
     p.y = out; p.ldy = ldo;
     if ((p.ldy & 3) || (reinterpret_cast<uintptr_t>(p.y) & 15)) {
       set_error("mlp_forward: output width %lld must be a multiple of 4 floats and 16-byte aligned", (long long)p.ldy);
       return LCREC_ERR_UNSUPPORTED;
     }
     { ProfScope prof(1 + std::min(l, 15), st); LC_TRY(launch_linear(p, st)); }
-    if (!last) {
-      ProfScope prof(17, st);
-      LC_TRY(launch_split_f16(out, n_rows, m->dims[l + 1], ldo, hid_hi, hid_lo, ld8(m->dims[l + 1]), rscale, st));
-      a_hi = hid_hi; a_lo = hid_lo; lda = ld8(m->dims[l + 1]);
-    }
+    cur = out; ldc = ldo;
   }
   if (acts && acts[m->n_layers - 1] && acts[m->n_layers - 1] != y)
     LC_CUDA(cudaMemcpyAsync(acts[m->n_layers - 1], y, sizeof(float) * n_rows * m->dims[m->n_layers], cudaMemcpyDeviceToDevice, st));
@@ -650,7 +708,7 @@ extern "C" int lcrec_mlp_forward(lcrec_mlp_t* m, const float* x, int64_t n_rows,
 // variant: bit 0 = alternative tile for wide N, bit 1 = f16 x3 engine instead of tf32 x3.
 extern "C" int64_t lcrec_linear_workspace_bytes(int64_t n_rows, int k_in, int n_out) {
   return 2 * arena_need(sizeof(float) * n_rows * ld4(k_in)) + 2 * arena_need(sizeof(float) * (int64_t)n_out * ld4(k_in)) +
-         arena_need(sizeof(float) * n_rows) + arena_need(sizeof(float) * n_out) + 1024;
+         arena_need(sizeof(float) * n_rows * std::max<int64_t>(1, ceil_div(ld8(k_in), 128))) + arena_need(sizeof(float) * n_out) + 1024;
 }
 extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* w, const float* b,
                                     int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,
@@ -665,6 +723,21 @@ extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, co
   LinearProblem p{};
   p.n_rows = n_rows; p.k = k_in; p.n_out = n_out; p.bias = b; p.relu = relu;
   p.y = y; p.ldy = n_out; p.acc_chunk = acc_chunk; p.variant = variant & 1;
+  if ((variant & 6) == 6) {      // CTA-pair kernel, group-scaled activations (n_out must be a multiple of 256)
+    const int64_t ldk = ld8(k_in);
+    __half* a_hi = ar.take<__half>(n_rows * ldk); __half* a_lo = ar.take<__half>(n_rows * ldk);
+    __half* w_hi = ar.take<__half>((int64_t)n_out * ldk); __half* w_lo = ar.take<__half>((int64_t)n_out * ldk);
+    float* cs = ar.take<float>(n_out);
+    float* as = ar.take<float>(n_rows * ceil_div(ldk, kPairGroup));
+    if (!ar.ok()) { set_error("linear_forward: workspace too small"); return LCREC_ERR_NOMEM; }
+    LC_TRY(launch_split_groups(x, n_rows, k_in, k_in, a_hi, a_lo, ldk, as, n_rows, st));
+    LC_TRY(launch_split_f16(w, n_out, k_in, k_in, w_hi, w_lo, ldk, cs, st));
+    PairProblem q{};
+    q.a.hi = a_hi; q.a.lo = a_lo; q.a.ld = ldk; q.a.inv_scale = as; q.a.ld_scale = n_rows; q.a.group = kPairGroup;
+    q.n_rows = n_rows; q.k = k_in; q.w_hi = w_hi; q.w_lo = w_lo; q.ldw = ldk; q.w_inv_scale = cs; q.n_out = n_out;
+    q.bias = b; q.relu = relu; q.y = y; q.ldy = n_out; q.debug = (variant & 1) ? 4 : 0;
+    return launch_linear_pair(q, st);
+  }
   if (variant & 2) {
     const int64_t ldk = ld8(k_in);
     __half* a_hi = ar.take<__half>(n_rows * ldk); __half* a_lo = ar.take<__half>(n_rows * ldk);

@@ -109,6 +109,11 @@ class MlpHandle:
     def set_variant(self, v: int) -> None:
         _lib.check(self.lib.lcrec_mlp_set_variant(self.handle, int(v)))
 
+    def set_trace(self, buf: Optional[torch.Tensor]) -> None:
+        """Measurement only: int64 CUDA tensor of 4*512*4 elements receiving pipeline clock stamps, or None."""
+        self._trace = buf
+        _lib.check(self.lib.lcrec_mlp_set_trace(self.handle, _p(buf)))
+
     def forward(self, x: torch.Tensor, want_acts: bool = False):
         _need_cuda(x)
         x2 = _f32c(x.reshape(-1, self.dims[0]))
