@@ -36,11 +36,14 @@ __device__ __forceinline__ double block_sum_double(double v, double* scratch) {
   return t;  // valid in warp 0
 }
 
-// smem layout: for each staged level: codebook (k*D floats) then norms (k floats)
-template <int D>
-__global__ void __launch_bounds__(kRqThreads, 1) rq_quantize_smem_kernel(const RqArgs a) {
+// smem layout: for each staged level: codebook (k*D floats) then norms (k floats).
+// IPT items per thread share every broadcast codebook load (one LDS.128 feeds 4 * IPT FMAs: with one item per
+// thread the kernel is bound by shared-memory instruction issue, not by the FMA pipe); TRAIN adds the
+// straight-through x_q and the per-level squared errors of the training forward.
+template <int D, int IPT, bool TRAIN>
+__global__ void __launch_bounds__(kRqThreads * IPT, 1) rq_quantize_smem_kernel(const RqArgs a) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[kRqThreads / 32];
+  __shared__ double red[kRqThreads * IPT / 32];
   float* cbs[LCREC_MAX_LEVELS];
   float* nrm[LCREC_MAX_LEVELS];
   {
@@ -62,82 +65,116 @@ __global__ void __launch_bounds__(kRqThreads, 1) rq_quantize_smem_kernel(const R
     }
   __syncthreads();
 
-  double err[LCREC_MAX_LEVELS];
+  double err[TRAIN ? LCREC_MAX_LEVELS : 1];
 #pragma unroll
-  for (int l = 0; l < LCREC_MAX_LEVELS; ++l) err[l] = 0.0;
+  for (int l = 0; l < (TRAIN ? LCREC_MAX_LEVELS : 1); ++l) err[l] = 0.0;
 
-  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < a.n;
-       item += (int64_t)gridDim.x * blockDim.x) {
-    float r[D], xq[D];
-    const float4* zp = reinterpret_cast<const float4*>(a.z + item * D);
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x * IPT; base < a.n; base += (int64_t)gridDim.x * blockDim.x * IPT) {
+    int64_t item[IPT]; bool ok[IPT];
+    float r[IPT][D];
+    float xq[TRAIN ? IPT : 1][TRAIN ? D : 1];
 #pragma unroll
-    for (int d = 0; d < D / 4; ++d) {
-      const float4 t = __ldg(zp + d);
-      r[4 * d] = t.x; r[4 * d + 1] = t.y; r[4 * d + 2] = t.z; r[4 * d + 3] = t.w;
+    for (int j = 0; j < IPT; ++j) {
+      item[j] = base + (int64_t)j * blockDim.x + threadIdx.x;
+      ok[j] = item[j] < a.n;
+      const float4* zp = reinterpret_cast<const float4*>(a.z + (ok[j] ? item[j] : 0) * D);
+#pragma unroll
+      for (int d = 0; d < D / 4; ++d) {
+        const float4 t = __ldg(zp + d);
+        r[j][4 * d] = t.x; r[j][4 * d + 1] = t.y; r[j][4 * d + 2] = t.z; r[j][4 * d + 3] = t.w;
+      }
+      if constexpr (TRAIN) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) xq[j][d] = 0.f;
+      }
     }
-#pragma unroll
-    for (int d = 0; d < D; ++d) xq[d] = 0.f;
 #pragma unroll 1
     for (int l = 0; l < a.n_levels_run; ++l) {
-      if (a.resid_last != nullptr && l == a.resid_level) {
-        float4* rp = reinterpret_cast<float4*>(a.resid_last + item * D);
+      float xx[IPT], best[IPT]; int best_k[IPT];
 #pragma unroll
-        for (int d = 0; d < D / 4; ++d) rp[d] = make_float4(r[4 * d], r[4 * d + 1], r[4 * d + 2], r[4 * d + 3]);
+      for (int j = 0; j < IPT; ++j) {
+        if (a.resid_last != nullptr && l == a.resid_level && ok[j]) {
+          float4* rp = reinterpret_cast<float4*>(a.resid_last + item[j] * D);
+#pragma unroll
+          for (int d = 0; d < D / 4; ++d) rp[d] = make_float4(r[j][4 * d], r[j][4 * d + 1], r[j][4 * d + 2], r[j][4 * d + 3]);
+        }
+        xx[j] = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) xx[j] = fmaf(r[j][d], r[j][d], xx[j]);
+        best[j] = INFINITY; best_k[j] = 0;
       }
-      float xx = 0.f;
-#pragma unroll
-      for (int d = 0; d < D; ++d) xx = fmaf(r[d], r[d], xx);
       const float* cb = cbs[l];
       const float* nr = nrm[l];
-      float best = INFINITY;
-      int best_k = 0;
       const int kl = a.k[l];
 #pragma unroll 2
       for (int c = 0; c < kl; ++c) {
         const float4* cp = reinterpret_cast<const float4*>(cb + c * D);
-        float dot0 = 0.f, dot1 = 0.f;
+        float dot0[IPT], dot1[IPT];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) { dot0[j] = 0.f; dot1[j] = 0.f; }
 #pragma unroll
         for (int d = 0; d < D / 4; d += 2) {
           const float4 u = cp[d];
-          dot0 = fmaf(r[4 * d], u.x, dot0); dot0 = fmaf(r[4 * d + 1], u.y, dot0);
-          dot0 = fmaf(r[4 * d + 2], u.z, dot0); dot0 = fmaf(r[4 * d + 3], u.w, dot0);
+#pragma unroll
+          for (int j = 0; j < IPT; ++j) {
+            dot0[j] = fmaf(r[j][4 * d], u.x, dot0[j]); dot0[j] = fmaf(r[j][4 * d + 1], u.y, dot0[j]);
+            dot0[j] = fmaf(r[j][4 * d + 2], u.z, dot0[j]); dot0[j] = fmaf(r[j][4 * d + 3], u.w, dot0[j]);
+          }
           if (d + 1 < D / 4) {
             const float4 w = cp[d + 1];
-            dot1 = fmaf(r[4 * d + 4], w.x, dot1); dot1 = fmaf(r[4 * d + 5], w.y, dot1);
-            dot1 = fmaf(r[4 * d + 6], w.z, dot1); dot1 = fmaf(r[4 * d + 7], w.w, dot1);
+#pragma unroll
+            for (int j = 0; j < IPT; ++j) {
+              dot1[j] = fmaf(r[j][4 * d + 4], w.x, dot1[j]); dot1[j] = fmaf(r[j][4 * d + 5], w.y, dot1[j]);
+              dot1[j] = fmaf(r[j][4 * d + 6], w.z, dot1[j]); dot1[j] = fmaf(r[j][4 * d + 7], w.w, dot1[j]);
+            }
           }
         }
-        const float dist = (xx + nr[c]) - 2.f * (dot0 + dot1);
-        if (dist < best) { best = dist; best_k = c; }
+        const float nc = nr[c];
+#pragma unroll
+        for (int j = 0; j < IPT; ++j) {
+          const float dist = (xx[j] + nc) - 2.f * (dot0[j] + dot1[j]);
+          if (dist < best[j]) { best[j] = dist; best_k[j] = c; }
+        }
       }
-      if (a.codes) a.codes[item * a.n_levels + l] = best_k;
-      const float* q = cb + best_k * D;
-      double e = 0.0;
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const float t = q[d] - r[d];
-        e += (double)(t * t);
-        const float xres = r[d] + t;
-        r[d] = r[d] - xres;
-        xq[d] += xres;
+      for (int j = 0; j < IPT; ++j) {
+        if (a.codes && ok[j]) a.codes[item[j] * a.n_levels + l] = best_k[j];
+        const float* q = cb + best_k[j] * D;
+        double e = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float t = q[d] - r[j][d];
+          if constexpr (TRAIN) e += (double)(t * t);
+          const float xres = r[j][d] + t;
+          r[j][d] = r[j][d] - xres;
+          if constexpr (TRAIN) xq[j][d] += xres;
+        }
+        if constexpr (TRAIN) { if (ok[j]) err[l] += e; }
       }
-      err[l] += e;
     }
-    if (a.resid_last != nullptr && a.resid_level >= a.n_levels_run) {
-      float4* rp = reinterpret_cast<float4*>(a.resid_last + item * D);
 #pragma unroll
-      for (int d = 0; d < D / 4; ++d) rp[d] = make_float4(r[4 * d], r[4 * d + 1], r[4 * d + 2], r[4 * d + 3]);
-    }
-    if (a.xq) {
-      float4* xp = reinterpret_cast<float4*>(a.xq + item * D);
+    for (int j = 0; j < IPT; ++j) {
+      if (!ok[j]) continue;
+      if (a.resid_last != nullptr && a.resid_level >= a.n_levels_run) {
+        float4* rp = reinterpret_cast<float4*>(a.resid_last + item[j] * D);
 #pragma unroll
-      for (int d = 0; d < D / 4; ++d) xp[d] = make_float4(xq[4 * d], xq[4 * d + 1], xq[4 * d + 2], xq[4 * d + 3]);
+        for (int d = 0; d < D / 4; ++d) rp[d] = make_float4(r[j][4 * d], r[j][4 * d + 1], r[j][4 * d + 2], r[j][4 * d + 3]);
+      }
+      if constexpr (TRAIN) {
+        if (a.xq) {
+          float4* xp = reinterpret_cast<float4*>(a.xq + item[j] * D);
+#pragma unroll
+          for (int d = 0; d < D / 4; ++d) xp[d] = make_float4(xq[j][4 * d], xq[j][4 * d + 1], xq[j][4 * d + 2], xq[j][4 * d + 3]);
+        }
+      }
     }
   }
-  if (a.sq_err) {
-    for (int l = 0; l < a.n_levels_run; ++l) {
-      const double t = block_sum_double(err[l], red);
-      if (threadIdx.x == 0) atomicAdd(a.sq_err + l, t);
+  if constexpr (TRAIN) {
+    if (a.sq_err) {
+      for (int l = 0; l < a.n_levels_run; ++l) {
+        const double t = block_sum_double(err[l], red);
+        if (threadIdx.x == 0) atomicAdd(a.sq_err + l, t);
+      }
     }
   }
 }
@@ -233,14 +270,22 @@ __global__ void vq_distances_kernel(const float* __restrict__ r, int64_t n, int 
   }
 }
 
-template <int D>
-static int launch_rq_smem(const RqArgs& a, size_t smem, cudaStream_t st) {
+template <int D, int IPT, bool TRAIN>
+static int launch_rq_smem_impl(const RqArgs& a, size_t smem, cudaStream_t st) {
   static bool attr = false;
-  if (!attr) { LC_CUDA(cudaFuncSetAttribute(rq_quantize_smem_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
-  const int64_t blocks = std::min<int64_t>(ceil_div(a.n, kRqThreads), (int64_t)num_sms());
-  rq_quantize_smem_kernel<D><<<(unsigned)blocks, kRqThreads, smem, st>>>(a);
+  auto kern = rq_quantize_smem_kernel<D, IPT, TRAIN>;
+  if (!attr) { LC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
+  const int threads = kRqThreads * IPT;
+  const int64_t blocks = std::min<int64_t>(ceil_div(a.n, threads * IPT), (int64_t)num_sms());
+  kern<<<(unsigned)blocks, threads, smem, st>>>(a);
   LC_LAUNCH_CHECK("rq_quantize_smem_kernel");
   return LCREC_OK;
+}
+template <int D>
+static int launch_rq_smem(const RqArgs& a, size_t smem, cudaStream_t st) {
+  if (a.xq != nullptr || a.sq_err != nullptr) return launch_rq_smem_impl<D, 1, true>(a, smem, st);
+  if constexpr (D <= 32) { if (a.n >= 4096) return launch_rq_smem_impl<D, 2, false>(a, smem, st); }
+  return launch_rq_smem_impl<D, 1, false>(a, smem, st);
 }
 
 }  // namespace lcrec

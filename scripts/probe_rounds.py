@@ -22,7 +22,7 @@ ix = G.build_indexer(model, n)
 ix.pass0(x)
 codes0 = ix.codes_view(n).clone(); resid = ix.resid_view(n).clone()
 cbt = model.rq.vq_layers[-1].embedding.weight.detach()
-for mode in (2, 1, 0):
+for mode in [int(m) for m in os.environ.get("SK_MODES", "2,1,0").split(",")]:
     ops.sinkhorn_set_mode(mode)
     codes = codes0.clone()
     tot = 0.0
@@ -47,5 +47,5 @@ for mode in (2, 1, 0):
         lit = codes.clone()
     elif mode == 2:
         hyb = codes.clone()
-print("filtered final codes == literal final codes:", bool(torch.equal(lit, hyb)))
+if "lit" in dir() and "hyb" in dir(): print("filtered final codes == literal final codes:", bool(torch.equal(lit, hyb)))
 ops.sinkhorn_set_mode(2)
