@@ -147,6 +147,20 @@ int64_t lcrec_collisions_workspace_bytes(int64_t n);
 int lcrec_collisions(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes,
                      int64_t* offsets /* n+1 */, int64_t* members /* n */, int64_t* counts,
                      void* ws, int64_t ws_bytes, void* stream);
+/* Prefix segments: runs (>= 2 items) of equal first n_levels-1 codes, same CSR / counts layout as lcrec_collisions.
+ * While the collision rounds rewrite the last level only (generate_indices.py:116-119 re-assigns with use_sk on the
+ * last level), two items can collide only inside one segment; built once after PASS 0. */
+int lcrec_prefix_segments(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes,
+                          int64_t* seg_offsets /* n+1 */, int64_t* seg_members /* n */, int64_t* counts,
+                          void* ws, int64_t ws_bytes, void* stream);
+/* Collision groups of codes[:, level] inside those segments (no global sort): same outputs as lcrec_collisions
+ * (group order differs; members of a group are in ascending item order).  counts: 8 int64, counts[5] = 1 when a
+ * segment was too large for the on-chip sort (> 1024 items): result incomplete, call lcrec_collisions instead. */
+int64_t lcrec_segment_collisions_workspace_bytes(int64_t max_segments);
+int lcrec_collisions_in_segments(const int64_t* codes, int64_t n, int n_levels, int level,
+                                 const int64_t* seg_offsets, const int64_t* seg_members, const int64_t* n_segs_dev,
+                                 int64_t max_segments, int64_t* offsets, int64_t* members, int64_t* counts,
+                                 void* ws, int64_t ws_bytes, void* stream);
 /* sorted (key, item) pairs only; keys_out/items_out (n) */
 int lcrec_sort_codes(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes,
                      uint64_t* keys_out, uint32_t* items_out, void* ws, int64_t ws_bytes, void* stream);
@@ -172,6 +186,13 @@ int lcrec_indexer_run_host(lcrec_indexer_t* ix, const float* x_host, int64_t n, 
 /* building blocks of the loop, for multi-GPU drivers and tests */
 int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t n, int64_t row_offset, void* stream);
 int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* counts_host, void* stream);
+/* The collision rounds alone (generate_indices.py:108-128) on caller-owned device arrays: codes (n, L) int64 updated
+ * in place, resid (n, e_dim) = residual entering the last level; n <= max_items.  stats_host as in run_host. */
+int lcrec_indexer_resolve(lcrec_indexer_t* ix, int64_t* codes, const float* resid, int64_t n, int max_rounds,
+                          int64_t* stats_host, void* stream);
+/* 1 (default): from the second round on, collisions are searched inside the prefix segments (no global re-sort);
+ * 0: every round re-sorts all items.  Results are identical; process-wide switch for cross-checks. */
+int lcrec_indexer_set_segments(int on);
 int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
 float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).

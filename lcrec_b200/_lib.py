@@ -49,6 +49,9 @@ SIGNATURES = {
     "lcrec_collisions_workspace_bytes": (i64, [i64]),
     "lcrec_collisions": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, vp, i64, vp]),
     "lcrec_sort_codes": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, i64, vp]),
+    "lcrec_prefix_segments": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, vp, i64, vp]),
+    "lcrec_segment_collisions_workspace_bytes": (i64, [i64]),
+    "lcrec_collisions_in_segments": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
     "lcrec_profile_enable": (C.c_int, [C.c_int]),
     "lcrec_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64)]),
     "lcrec_indexer_create": (C.c_int, [vp, C.c_int, C.c_int, pp, C.POINTER(i32), f64, C.c_int, i64, i64, pp]),
@@ -57,6 +60,8 @@ SIGNATURES = {
     "lcrec_indexer_run_host": (C.c_int, [vp, vp, i64, C.c_int, vp, C.POINTER(i64), vp]),
     "lcrec_indexer_pass0": (C.c_int, [vp, vp, i64, i64, vp]),
     "lcrec_indexer_round": (C.c_int, [vp, i64, C.POINTER(i64), vp]),
+    "lcrec_indexer_resolve": (C.c_int, [vp, vp, vp, i64, C.c_int, C.POINTER(i64), vp]),
+    "lcrec_indexer_set_segments": (C.c_int, [C.c_int]),
     "lcrec_indexer_codes": (vp, [vp]),
     "lcrec_indexer_resid": (vp, [vp]),
 }

@@ -132,6 +132,8 @@ struct lcrec_indexer {
   int64_t* offsets = nullptr; int64_t* members = nullptr; int64_t* counts = nullptr; int32_t* flags = nullptr;
   void* col_ws = nullptr; int64_t col_ws_bytes = 0;
   void* sk_ws = nullptr; int64_t sk_ws_bytes = 0;
+  int64_t* seg_offsets = nullptr; int64_t* seg_members = nullptr; int64_t* seg_counts = nullptr;   // prefix segments
+  void* seg_ws = nullptr; int64_t seg_ws_bytes = 0;
   float* stage[2] = {nullptr, nullptr};
   int64_t* counts_host = nullptr;   // pinned: 4 counts + flags
   cudaStream_t copy_stream = nullptr;
@@ -175,6 +177,11 @@ extern "C" int lcrec_indexer_create(lcrec_mlp_t* encoder, int e_dim, int n_level
   IX_ALLOC(ix->col_ws, ix->col_ws_bytes);
   ix->sk_ws_bytes = lcrec_sinkhorn_groups_workspace_bytes(max_items, n_codes[n_levels - 1]);
   IX_ALLOC(ix->sk_ws, ix->sk_ws_bytes);
+  IX_ALLOC(ix->seg_offsets, sizeof(int64_t) * (max_items + 1));
+  IX_ALLOC(ix->seg_members, sizeof(int64_t) * max_items);
+  IX_ALLOC(ix->seg_counts, sizeof(int64_t) * 8);
+  ix->seg_ws_bytes = lcrec_segment_collisions_workspace_bytes(max_items / 2 + 1);
+  IX_ALLOC(ix->seg_ws, ix->seg_ws_bytes);
   if (cudaMallocHost((void**)&ix->counts_host, sizeof(int64_t) * 8) != cudaSuccess) {
     set_error("indexer: cudaMallocHost failed"); lcrec_indexer_destroy(ix); return LCREC_ERR_NOMEM;
   }
@@ -186,6 +193,7 @@ extern "C" int lcrec_indexer_destroy(lcrec_indexer_t* ix) {
   if (!ix) return LCREC_OK;
   cudaFree(ix->codes); cudaFree(ix->resid); cudaFree(ix->z); cudaFree(ix->mlp_ws); cudaFree(ix->offsets);
   cudaFree(ix->members); cudaFree(ix->counts); cudaFree(ix->col_ws); cudaFree(ix->sk_ws);
+  cudaFree(ix->seg_offsets); cudaFree(ix->seg_members); cudaFree(ix->seg_counts); cudaFree(ix->seg_ws);
   cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
   if (ix->counts_host) cudaFreeHost(ix->counts_host);
   for (int i = 0; i < 2; ++i) { if (ix->ev_copied[i]) cudaEventDestroy(ix->ev_copied[i]); if (ix->ev_consumed[i]) cudaEventDestroy(ix->ev_consumed[i]); }
@@ -213,54 +221,107 @@ extern "C" int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t 
   return LCREC_OK;
 }
 
-// One check (+ resolve when `resolve`): counts_host receives [n_unique, n_groups, rows, max_mult, flags]
-static int indexer_check(lcrec_indexer_t* ix, int64_t n, bool resolve, int64_t* counts_host, cudaStream_t st) {
+static int g_use_segments = 1;
+// 1 (default): after the first round the collision check runs inside the prefix segments (no global re-sort);
+// 0: every round re-sorts all items (the original path; used to cross-check).
+extern "C" int lcrec_indexer_set_segments(int on) { g_use_segments = on ? 1 : 0; return LCREC_OK; }
+
+// One collision check of codes (n x L) into ix->offsets / members / counts, counts copied to the pinned host block
+// (8 int64: n_unique, n_groups, rows, max_mult, flag words, segment fallback).  Synchronises the stream.
+static int collide_and_fetch(lcrec_indexer_t* ix, const int64_t* codes, int64_t n, bool in_segments, cudaStream_t st) {
   {
     ProfScope prof(21, st);
-    LC_TRY(lcrec_collisions(ix->codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
-                            ix->col_ws_bytes, st));
+    if (in_segments)
+      LC_TRY(lcrec_collisions_in_segments(codes, n, ix->L, ix->L - 1, ix->seg_offsets, ix->seg_members, ix->seg_counts + 1,
+                                          n / 2 + 1, ix->offsets, ix->members, ix->counts, ix->seg_ws, ix->seg_ws_bytes, st));
+    else
+      LC_TRY(lcrec_collisions(codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
+                              ix->col_ws_bytes, st));
   }
-  LC_CUDA(cudaMemsetAsync(ix->flags, 0, sizeof(int32_t) * 2, st));
-  LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 5, cudaMemcpyDeviceToHost, st));
+  LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 6, cudaMemcpyDeviceToHost, st));
   LC_CUDA(cudaStreamSynchronize(st));
+  return LCREC_OK;
+}
+
+static int check_flags(int32_t f) {
+  if (f & 2) { set_error("indexer: workspace for oversized collision groups exhausted"); return LCREC_ERR_NOMEM; }
+  if (f & 4) { set_error("indexer: amplitude > 0 failed (vq.py:59)"); return LCREC_ERR_NUMERIC; }
+  return LCREC_OK;
+}
+
+// generate_indices.py:108-128 on codes (n x L, device, updated in place) with the residuals entering the last level.
+static int rounds_impl(lcrec_indexer_t* ix, int64_t* codes, const float* resid, int64_t n, int max_rounds, int64_t* stats,
+                       cudaStream_t st) {
+  int64_t rounds = 0, g1 = 0, r1 = 0, tot_rows = 0;
+  bool use_seg = g_use_segments && ix->L >= 2, have_seg = false;
+  LC_CUDA(cudaMemsetAsync(ix->counts, 0, sizeof(int64_t) * 8, st));     // incl. the flag words (accumulated by atomicOr)
+  const int64_t* c = ix->counts_host;
+  while (true) {
+    const bool resolve = rounds < max_rounds;
+    LC_TRY(collide_and_fetch(ix, codes, n, have_seg, st));
+    if (have_seg && c[5] != 0) {            // a segment too large for the on-chip sort: back to the global sort for good
+      have_seg = use_seg = false;
+      LC_CUDA(cudaMemsetAsync(ix->counts + 5, 0, sizeof(int64_t), st));
+      LC_TRY(collide_and_fetch(ix, codes, n, false, st));
+    }
+    LC_TRY(check_flags((int32_t)(c[4] & 0xffffffff)));
+    const int64_t groups = c[1], rows = c[2];
+    if (c[0] == n || !resolve || groups == 0) break;
+    if (rounds == 0) { g1 = groups; r1 = rows; }
+    if (use_seg && !have_seg) {
+      ProfScope prof(21, st);
+      LC_TRY(lcrec_prefix_segments(codes, n, ix->L, ix->K.data(), ix->seg_offsets, ix->seg_members, ix->seg_counts, ix->col_ws,
+                                   ix->col_ws_bytes, st));
+      have_seg = true;
+    }
+    {
+      ProfScope prof(22, st);
+      LC_TRY(lcrec_sinkhorn_groups(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
+                                   ix->counts + 1, groups, rows, ix->eps, ix->iters, codes, ix->L, ix->L - 1,
+                                   ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));
+    }
+    tot_rows += rows;
+    ++rounds;
+  }
+  int32_t f[2];
+  LC_CUDA(cudaMemcpyAsync(f, ix->flags, sizeof(f), cudaMemcpyDeviceToHost, st));
+  LC_CUDA(cudaStreamSynchronize(st));
+  LC_TRY(check_flags(f[0]));
+  if (stats) {
+    stats[0] = rounds; stats[1] = c[0]; stats[2] = g1; stats[3] = r1; stats[4] = tot_rows; stats[5] = c[3];
+    stats[6] = f[0] & 1; stats[7] = 0;
+  }
+  return LCREC_OK;
+}
+
+static int indexer_rounds(lcrec_indexer_t* ix, int64_t n, int max_rounds, int64_t* stats, cudaStream_t st) {
+  return rounds_impl(ix, ix->codes, ix->resid, n, max_rounds, stats, st);
+}
+
+// The collision rounds alone on caller-owned device arrays (codes n x L updated in place; resid n x e_dim = residual
+// entering the last level).  stats_host as in lcrec_indexer_run_host.
+extern "C" int lcrec_indexer_resolve(lcrec_indexer_t* ix, int64_t* codes, const float* resid, int64_t n, int max_rounds,
+                                     int64_t* stats_host, void* stream) {
+  LC_ARG(ix && n >= 0 && n <= ix->max_items && max_rounds >= 0);
+  if (n == 0) { if (stats_host) memset(stats_host, 0, 8 * sizeof(int64_t)); return LCREC_OK; }
+  LC_ARG(codes && resid);
+  return rounds_impl(ix, codes, resid, n, max_rounds, stats_host, (cudaStream_t)stream);
+}
+
+// One round on the indexer's own table (teacher-forced parity tests): check + resolve; counts_host (4 int64).
+extern "C" int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* counts_host, void* stream) {
+  LC_ARG(ix && n >= 0 && n <= ix->max_items);
+  cudaStream_t st = (cudaStream_t)stream;
+  LC_CUDA(cudaMemsetAsync(ix->counts, 0, sizeof(int64_t) * 8, st));
+  LC_TRY(collide_and_fetch(ix, ix->codes, n, false, st));
   const int64_t groups = ix->counts_host[1], rows = ix->counts_host[2];
-  if (resolve && groups > 0) {
+  if (groups > 0) {
     ProfScope prof(22, st);
     LC_TRY(lcrec_sinkhorn_groups(ix->resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
                                  ix->counts + 1, groups, rows, ix->eps, ix->iters, ix->codes, ix->L, ix->L - 1,
                                  ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));
   }
   if (counts_host) memcpy(counts_host, ix->counts_host, sizeof(int64_t) * 4);
-  return LCREC_OK;
-}
-
-extern "C" int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* counts_host, void* stream) {
-  LC_ARG(ix && n >= 0 && n <= ix->max_items);
-  return indexer_check(ix, n, true, counts_host, (cudaStream_t)stream);
-}
-
-static int indexer_rounds(lcrec_indexer_t* ix, int64_t n, int max_rounds, int64_t* stats, cudaStream_t st) {
-  int64_t c[4] = {0, 0, 0, 0};
-  int64_t rounds = 0, g1 = 0, r1 = 0, tot_rows = 0;
-  int32_t flags_acc = 0;
-  while (true) {                                     // generate_indices.py:108-128
-    const bool resolve = rounds < max_rounds;
-    LC_TRY(indexer_check(ix, n, resolve, c, st));
-    if (c[0] == n || !resolve) break;
-    if (rounds == 0) { g1 = c[1]; r1 = c[2]; }
-    tot_rows += c[2];
-    ++rounds;
-    int32_t f[2];
-    LC_CUDA(cudaMemcpyAsync(f, ix->flags, sizeof(f), cudaMemcpyDeviceToHost, st));
-    LC_CUDA(cudaStreamSynchronize(st));
-    flags_acc |= f[0];
-    if (f[0] & 2) { set_error("indexer: workspace for oversized collision groups exhausted"); return LCREC_ERR_NOMEM; }
-    if (f[0] & 4) { set_error("indexer: amplitude > 0 failed (vq.py:59)"); return LCREC_ERR_NUMERIC; }
-  }
-  if (stats) {
-    stats[0] = rounds; stats[1] = c[0]; stats[2] = g1; stats[3] = r1; stats[4] = tot_rows; stats[5] = c[3];
-    stats[6] = flags_acc & 1; stats[7] = 0;
-  }
   return LCREC_OK;
 }
 

@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
 
 // flags on the sorted keys: low 32 bits = item belongs to a run of length >= 2, high 32 bits = item
 // is the head of such a run.  Packed so that one scan yields member positions and group ids.
-__global__ void run_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t* __restrict__ flags) {
+__global__ void run_flags_kernel(const uint64_t* __restrict__ keys, int64_t n, uint64_t* __restrict__ flags, int drop_bits) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t k = keys[i];
-    const bool eq_prev = i > 0 && keys[i - 1] == k;
-    const bool eq_next = i + 1 < n && keys[i + 1] == k;
+    const uint64_t k = keys[i] >> drop_bits;        // drop_bits > 0: runs of equal PREFIX (low digits ignored)
+    const bool eq_prev = i > 0 && (keys[i - 1] >> drop_bits) == k;
+    const bool eq_next = i + 1 < n && (keys[i + 1] >> drop_bits) == k;
     flags[i] = (uint64_t)((eq_prev || eq_next) ? 1u : 0u) | ((uint64_t)((!eq_prev && eq_next) ? 1u : 0u) << 32);
   }
 }
@@ -221,6 +221,160 @@ __global__ void max_mult_kernel(const int64_t* offsets, const int64_t* counts_in
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax((long long*)(counts + 3), m);
 }
 
+
+// ---------------------------------------------------------------------------- collisions inside prefix segments
+// While the rounds rewrite the last level only, two items can collide only if they share a prefix segment
+// (lcrec_prefix_segments, built once).  Per round: sort the members of every segment by (code of `level`, item);
+// runs of equal code with >= 2 members are the collision groups - no global re-sort.
+// Group slots and member slots are claimed TOGETHER with one 64-bit atomicAdd (groups in the high, rows in the low
+// word), which serialises the claims: the groups of claim k start exactly where the rows of claim k-1 end, so the
+// CSR stays consistent (offsets[g + 1] closes group g) although segments finish in arbitrary order (groups are
+// independent problems: their order changes no result; members of a group stay in ascending item order).
+// ctl: [0] packed (groups << 32 | rows) cursor, [1] max multiplicity, [2] number of big segments, [3] fallback flag.
+constexpr int kSegMax = 1024;     // largest segment sorted on chip; anything bigger raises the fallback flag
+__global__ void __launch_bounds__(256) segment_collisions_kernel(const int64_t* __restrict__ codes, int n_levels, int level,
+                                                                 const int64_t* __restrict__ seg_offsets,
+                                                                 const int64_t* __restrict__ seg_members,
+                                                                 const int64_t* __restrict__ n_segs_dev,
+                                                                 int64_t* __restrict__ offsets, int64_t* __restrict__ members,
+                                                                 unsigned long long* __restrict__ ctl, int32_t* __restrict__ big_list) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_segs = *n_segs_dev;
+  long long local_max = 0;
+  for (int64_t sg = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; sg < n_segs; sg += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t beg = seg_offsets[sg];
+    const int m = (int)min((int64_t)(kSegMax + 1), seg_offsets[sg + 1] - beg);
+    if (m > 32) {
+      if (lane == 0) {
+        if (m > kSegMax) atomicExch(ctl + 3, 1ull);
+        else big_list[atomicAdd(ctl + 2, 1ull)] = (int32_t)sg;
+      }
+      continue;
+    }
+    unsigned long long key = ~0ull;
+    if (lane < m) {
+      const int64_t item = seg_members[beg + lane];
+      key = ((unsigned long long)codes[item * n_levels + level] << 32) | (unsigned long long)item;
+    }
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)          // bitonic sort of the 32 keys held by the warp
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+        const bool take_min = ((lane & k) == 0) == ((lane & j) == 0);
+        key = take_min ? (key < other ? key : other) : (key > other ? key : other);
+      }
+    const unsigned code = (unsigned)(key >> 32);
+    const unsigned prev = __shfl_up_sync(0xffffffffu, code, 1), next = __shfl_down_sync(0xffffffffu, code, 1);
+    const bool valid = lane < m;
+    const bool eq_prev = valid && lane > 0 && prev == code;
+    const bool eq_next = valid && lane + 1 < m && next == code;
+    const unsigned in_run = __ballot_sync(0xffffffffu, eq_prev || eq_next);
+    const unsigned heads = __ballot_sync(0xffffffffu, !eq_prev && eq_next);
+    if (in_run == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(ctl, ((unsigned long long)__popc(heads) << 32) | (unsigned long long)__popc(in_run));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const int64_t rb = (int64_t)(base & 0xffffffffull), gb = (int64_t)(base >> 32);
+    const unsigned below = (1u << lane) - 1u;
+    if (eq_prev || eq_next) {
+      const int64_t pos = rb + __popc(in_run & below);
+      members[pos] = (int64_t)(key & 0xffffffffull);
+      if (!eq_prev) {
+        offsets[gb + __popc(heads & below)] = pos;
+        const unsigned after = lane == 31 ? 0u : ((in_run & ~heads) >> (lane + 1));    // followers of this head
+        local_max = max(local_max, (long long)__ffs(~after));
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if (lane == 0 && local_max > 0) atomicMax((long long*)(ctl + 1), local_max);
+}
+
+// segments of 33 .. kSegMax members: one CTA per segment, bitonic sort in shared memory
+__global__ void __launch_bounds__(256) segment_collisions_big_kernel(const int64_t* __restrict__ codes, int n_levels, int level,
+                                                                     const int64_t* __restrict__ seg_offsets,
+                                                                     const int64_t* __restrict__ seg_members,
+                                                                     int64_t* __restrict__ offsets, int64_t* __restrict__ members,
+                                                                     unsigned long long* __restrict__ ctl, const int32_t* __restrict__ big_list) {
+  __shared__ unsigned long long key[kSegMax];
+  __shared__ unsigned warp_rows[8], warp_heads[8];
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_big = (int)ctl[2];
+  long long local_max = 0;
+  for (int w = blockIdx.x; w < n_big; w += gridDim.x) {
+    const int64_t sg = big_list[w];
+    const int64_t beg = seg_offsets[sg];
+    const int m = (int)(seg_offsets[sg + 1] - beg);
+    __syncthreads();
+    for (int i = tid; i < kSegMax; i += 256) {
+      unsigned long long k = ~0ull;
+      if (i < m) { const int64_t item = seg_members[beg + i]; k = ((unsigned long long)codes[item * n_levels + level] << 32) | (unsigned long long)item; }
+      key[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= kSegMax; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < kSegMax; i += 256) {
+          const int p = i ^ j;
+          if (p > i) {
+            const unsigned long long a = key[i], b = key[p];
+            if (((i & k) == 0) == (a > b)) { key[i] = b; key[p] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    // thread t owns positions 4t .. 4t+3
+    unsigned rows = 0, heads = 0; bool run[4], head[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 4 * tid + e;
+      const unsigned c = (unsigned)(key[min(i, kSegMax - 1)] >> 32);
+      const bool eq_prev = i < m && i > 0 && (unsigned)(key[i - 1] >> 32) == c;
+      const bool eq_next = i + 1 < m && (unsigned)(key[i + 1] >> 32) == c;
+      run[e] = eq_prev || eq_next; head[e] = !eq_prev && eq_next;
+      rows += run[e]; heads += head[e];
+      if (head[e]) { int len = 1; while (i + len < m && (unsigned)(key[i + len] >> 32) == c) ++len; local_max = max(local_max, (long long)len); }
+    }
+    unsigned rinc = rows, hinc = heads;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned a = __shfl_up_sync(0xffffffffu, rinc, o), b = __shfl_up_sync(0xffffffffu, hinc, o);
+      if (lane >= o) { rinc += a; hinc += b; }
+    }
+    if (lane == 31) { warp_rows[warp] = rinc; warp_heads[warp] = hinc; }
+    __syncthreads();
+    unsigned rpre = 0, hpre = 0, rtot = 0, htot = 0;
+    for (int q = 0; q < 8; ++q) { if (q < warp) { rpre += warp_rows[q]; hpre += warp_heads[q]; } rtot += warp_rows[q]; htot += warp_heads[q]; }
+    if (tid == 0 && rtot > 0) s_base = atomicAdd(ctl, ((unsigned long long)htot << 32) | (unsigned long long)rtot);
+    __syncthreads();
+    if (rtot == 0) continue;
+    int64_t pos = (int64_t)(s_base & 0xffffffffull) + rpre + (rinc - rows);
+    int64_t gid = (int64_t)(s_base >> 32) + hpre + (hinc - heads);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (!run[e]) continue;
+      members[pos] = (int64_t)(key[4 * tid + e] & 0xffffffffull);
+      if (head[e]) offsets[gid++] = pos;
+      ++pos;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if (lane == 0 && local_max > 0) atomicMax((long long*)(ctl + 1), local_max);
+}
+
+// counts: [n_unique, n_groups, rows, max_multiplicity, -, fallback]; closes the CSR
+__global__ void segment_finish_kernel(const unsigned long long* __restrict__ ctl, int64_t n, int64_t* __restrict__ offsets,
+                                      int64_t* __restrict__ counts) {
+  const int64_t rows = (int64_t)(ctl[0] & 0xffffffffull), groups = (int64_t)(ctl[0] >> 32);
+  offsets[groups] = rows;
+  counts[0] = n - (rows - groups);
+  counts[1] = groups;
+  counts[2] = rows;
+  counts[3] = groups > 0 ? (int64_t)ctl[1] : (n > 0 ? 1 : 0);
+  counts[5] = (int64_t)ctl[3];
+}
+
 struct SortPlan { PackArgs pa; int total_bits; int n_tiles; };
 
 static int make_plan(int64_t n, int n_levels, const int32_t* n_codes, SortPlan* plan) {
@@ -290,8 +444,25 @@ extern "C" int lcrec_sort_codes(const int64_t* codes, int64_t n, int n_levels, c
   return LCREC_OK;
 }
 
+static int collisions_impl(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes, int drop_levels,
+                           int64_t* offsets, int64_t* members, int64_t* counts, void* ws, int64_t ws_bytes, void* stream);
+
 extern "C" int lcrec_collisions(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes, int64_t* offsets,
                                 int64_t* members, int64_t* counts, void* ws, int64_t ws_bytes, void* stream) {
+  return collisions_impl(codes, n, n_levels, n_codes, 0, offsets, members, counts, ws, ws_bytes, stream);
+}
+
+// Items that share their first n_levels - 1 codes (runs of >= 2): the only items that can ever collide while the
+// rounds rewrite the last level only.  Same CSR and counts layout as lcrec_collisions; members of a segment are
+// ordered by (last code, item).
+extern "C" int lcrec_prefix_segments(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes, int64_t* seg_offsets,
+                                     int64_t* seg_members, int64_t* counts, void* ws, int64_t ws_bytes, void* stream) {
+  LC_ARG(n_levels >= 2);
+  return collisions_impl(codes, n, n_levels, n_codes, 1, seg_offsets, seg_members, counts, ws, ws_bytes, stream);
+}
+
+static int collisions_impl(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes, int drop_levels,
+                           int64_t* offsets, int64_t* members, int64_t* counts, void* ws, int64_t ws_bytes, void* stream) {
   LC_ARG(n >= 0 && n_levels >= 1 && n_levels <= LCREC_MAX_LEVELS && n_codes && counts);
   LC_TRY(lcrec_device_check());
   cudaStream_t st = (cudaStream_t)stream;
@@ -310,8 +481,9 @@ extern "C" int lcrec_collisions(const int64_t* codes, int64_t n, int n_levels, c
   if (!ar.ok()) { set_error("collisions: workspace too small (%lld given, %lld needed)", (long long)ws_bytes, (long long)lcrec_collisions_workspace_bytes(n)); return LCREC_ERR_NOMEM; }
   uint64_t* ks; uint32_t* is;
   LC_TRY(sort_impl(codes, n, plan, k0, i0, k1, i1, hist, st, &ks, &is));
+  const int drop_bits = drop_levels > 0 ? plan.pa.shift[n_levels - 1 - drop_levels] : 0;   // level L-1 sits in the low bits
   const int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)num_sms() * 8);
-  run_flags_kernel<<<blocks, 256, 0, st>>>(ks, n, flags);
+  run_flags_kernel<<<blocks, 256, 0, st>>>(ks, n, flags, drop_bits);
   LC_LAUNCH_CHECK("run_flags_kernel");
   scan_reduce_kernel<<<(unsigned)sblocks, 256, 0, st>>>(flags, n, sums);
   LC_LAUNCH_CHECK("scan_reduce_kernel");
@@ -323,5 +495,39 @@ extern "C" int lcrec_collisions(const int64_t* codes, int64_t n, int n_levels, c
   LC_LAUNCH_CHECK("finish_counts_kernel");
   max_mult_kernel<<<std::max(1, std::min(blocks, 256)), 256, 0, st>>>(offsets, counts, counts);
   LC_LAUNCH_CHECK("max_mult_kernel");
+  return LCREC_OK;
+}
+
+extern "C" int64_t lcrec_segment_collisions_workspace_bytes(int64_t max_segments) {
+  return arena_need(64) + arena_need(4 * (max_segments + 1)) + 1024;
+}
+
+// Collision groups of the current codes[:, level] inside the prefix segments (see above).  counts (device, 8 int64):
+// [n_unique, n_groups, rows, max_multiplicity, -, fallback]; fallback = 1 means a segment was too large for the
+// on-chip sort and the result is incomplete: call lcrec_collisions instead.
+extern "C" int lcrec_collisions_in_segments(const int64_t* codes, int64_t n, int n_levels, int level, const int64_t* seg_offsets,
+                                            const int64_t* seg_members, const int64_t* n_segs_dev, int64_t max_segments,
+                                            int64_t* offsets, int64_t* members, int64_t* counts, void* ws, int64_t ws_bytes,
+                                            void* stream) {
+  LC_ARG(n >= 0 && n_levels >= 1 && level >= 0 && level < n_levels && max_segments >= 0 && counts);
+  LC_TRY(lcrec_device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  LC_ARG(codes && seg_offsets && seg_members && n_segs_dev && offsets && members);
+  Arena ar(ws, ws_bytes);
+  unsigned long long* ctl = ar.take<unsigned long long>(8);
+  int32_t* big_list = ar.take<int32_t>(max_segments + 1);
+  if (!ar.ok()) { set_error("collisions_in_segments: workspace too small"); return LCREC_ERR_NOMEM; }
+  LC_CUDA(cudaMemsetAsync(ctl, 0, 64, st));
+  if (max_segments > 0) {
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_segments, 8), (int64_t)num_sms() * 8));
+    segment_collisions_kernel<<<(unsigned)blocks, 256, 0, st>>>(codes, n_levels, level, seg_offsets, seg_members, n_segs_dev,
+                                                                 offsets, members, ctl, big_list);
+    LC_LAUNCH_CHECK("segment_collisions_kernel");
+    segment_collisions_big_kernel<<<(unsigned)std::min<int64_t>(max_segments, num_sms()), 256, 0, st>>>(
+        codes, n_levels, level, seg_offsets, seg_members, offsets, members, ctl, big_list);
+    LC_LAUNCH_CHECK("segment_collisions_big_kernel");
+  }
+  segment_finish_kernel<<<1, 1, 0, st>>>(ctl, n, offsets, counts);
+  LC_LAUNCH_CHECK("segment_finish_kernel");
   return LCREC_OK;
 }

@@ -89,6 +89,12 @@ class CudaBackend:
     def collisions(self, codes: torch.Tensor) -> dict:
         return self.ops.collisions(codes, self.n_codes)
 
+    def resolve_all(self, resid: torch.Tensor, codes: torch.Tensor, max_rounds: int):
+        """All rounds inside the library (lcrec_indexer_resolve); None when the table exceeds the indexer's capacity."""
+        if codes.shape[0] > self.indexer.max_items:
+            return None
+        return self.indexer.resolve_device(codes, resid.contiguous(), max_rounds)
+
     def resolve(self, resid: torch.Tensor, codes: torch.Tensor, info: dict) -> None:
         flags = self.ops.sinkhorn_groups(resid, self.cbs[-1], info["offsets"], info["members"],
                                          info["counts_dev"][1:2], info["n_groups"], info["n_rows"], self.eps,
@@ -110,6 +116,10 @@ def bucket_owner(codes: torch.Tensor, n_codes, world: int) -> torch.Tensor:
 def resolve_rounds(backend, codes: torch.Tensor, resid: torch.Tensor, max_rounds: int):
     """generate_indices.py:108-128 on one self-contained set of items (codes is updated in place)."""
     n = codes.shape[0]
+    if n > 0 and hasattr(backend, "resolve_all"):
+        st = backend.resolve_all(resid, codes, max_rounds)
+        if st is not None:
+            return {k: st[k] for k in ("rounds", "n_unique", "groups_round1", "rows_round1", "sinkhorn_rows", "max_multiplicity")}
     rounds = rows_total = 0
     first = (0, 0)
     info = {"n_unique": n, "max_multiplicity": 1 if n else 0}

@@ -257,6 +257,53 @@ def collisions(codes: torch.Tensor, n_codes: Sequence[int]):
             "n_groups": n_groups, "n_rows": n_rows, "max_multiplicity": max_mult, "counts_dev": counts}
 
 
+def prefix_segments(codes: torch.Tensor, n_codes: Sequence[int]):
+    """Runs (>= 2 items) of equal first L-1 codes, CSR like ``collisions`` (members ordered by (last code, item))."""
+    _need_cuda(codes)
+    lib = _lib.load()
+    c = codes.detach().to(torch.int64).contiguous()
+    n, L = c.shape
+    dev = c.device
+    offsets = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    members = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    counts = torch.zeros((8,), dtype=torch.int64, device=dev)
+    ws = _ws(lib.lcrec_collisions_workspace_bytes(n), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lcrec_prefix_segments(_p(c), n, L, _lib.i32_array(n_codes), _p(offsets), _p(members), _p(counts),
+                                             _p(ws), ws.numel(), _stream(c)))
+    _, n_segs, n_rows, max_size = [int(v) for v in counts[:4].tolist()]
+    return {"offsets": offsets[: n_segs + 1], "members": members[:n_rows], "n_segments": n_segs, "n_rows": n_rows,
+            "max_size": max_size, "counts_dev": counts}
+
+
+def collisions_in_segments(codes: torch.Tensor, segs: dict, level: Optional[int] = None):
+    """Collision groups of the current codes searched inside prefix segments (no global sort); same result dict as
+    ``collisions`` plus ``fallback`` (True: a segment exceeded the on-chip sort, use ``collisions``)."""
+    _need_cuda(codes)
+    lib = _lib.load()
+    c = codes.detach().to(torch.int64).contiguous()
+    n, L = c.shape
+    dev = c.device
+    level = L - 1 if level is None else level
+    offsets = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    members = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    counts = torch.zeros((8,), dtype=torch.int64, device=dev)
+    max_segs = segs["n_segments"]
+    ws = _ws(lib.lcrec_segment_collisions_workspace_bytes(max_segs), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lcrec_collisions_in_segments(_p(c), n, L, int(level), _p(segs["offsets"]), _p(segs["members"]),
+                                                    _p(segs["counts_dev"][1:2]), max_segs, _p(offsets), _p(members),
+                                                    _p(counts), _p(ws), ws.numel(), _stream(c)))
+    vals = [int(v) for v in counts.tolist()]
+    n_unique, n_groups, n_rows, max_mult = vals[:4]
+    return {"offsets": offsets[: n_groups + 1], "members": members[:n_rows], "n_unique": n_unique, "n_groups": n_groups,
+            "n_rows": n_rows, "max_multiplicity": max_mult, "counts_dev": counts, "fallback": bool(vals[5])}
+
+
+def indexer_set_segments(on: bool) -> None:
+    _lib.check(_lib.load().lcrec_indexer_set_segments(int(bool(on))))
+
+
 def sort_codes(codes: torch.Tensor, n_codes: Sequence[int]):
     _need_cuda(codes)
     lib = _lib.load()
@@ -341,6 +388,16 @@ class Indexer:
             _lib.check(self.lib.lcrec_indexer_run_host(self.handle, C.c_void_p(xt.data_ptr()), n, int(max_rounds),
                                                        C.c_void_p(out.data_ptr()), stats, st))
         return out, self._stats(stats)
+
+    def resolve_device(self, codes: torch.Tensor, resid: torch.Tensor, max_rounds: int = 20) -> dict:
+        """The collision rounds alone on caller-owned tensors (codes updated in place)."""
+        _need_cuda(codes, resid)
+        assert codes.dtype == torch.int64 and codes.is_contiguous() and resid.dtype == torch.float32 and resid.is_contiguous()
+        stats = (C.c_int64 * 8)()
+        with torch.cuda.device(codes.device):
+            _lib.check(self.lib.lcrec_indexer_resolve(self.handle, _p(codes), _p(resid), codes.shape[0], int(max_rounds),
+                                                      stats, _stream(codes)))
+        return self._stats(stats)
 
     def pass0(self, x: torch.Tensor, row_offset: int = 0) -> None:
         x2 = _f32c(x)

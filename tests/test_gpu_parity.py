@@ -270,6 +270,36 @@ def test_collisions_match_oracle(n, k, L):
     assert (np.diff(kk.astype(np.float64)) >= 0).all() and sorted(items.cpu().tolist()) == list(range(n))
 
 
+@pytest.mark.parametrize("n,k,L,seg", [(5, 4, 2, 2), (20000, 16, 3, 6), (200000, 256, 4, 5), (60000, 64, 4, 40), (9000, 8, 3, 700),
+                                       (5000, 4, 2, 1500)])
+def test_collisions_in_prefix_segments_match_global_sort(n, k, L, seg):
+    """The per-round collision search inside prefix segments == the global sort (groups as sets of member tuples),
+    for tiny segments (warp sort), segments of 33..1024 items (CTA sort) and the > 1024 fallback flag."""
+    rng = np.random.default_rng(n + seg)
+    n_par = max(n // seg, 1)
+    prefix = rng.integers(0, k, size=(n_par, L - 1))
+    codes = np.concatenate([prefix[rng.integers(0, n_par, size=n)], rng.integers(0, k, size=(n, 1))], axis=1).astype(np.int64)
+    segs = ops.prefix_segments(T(codes), [k] * L)
+    pre = O.collision_groups(codes[:, :-1])
+    assert segs["n_segments"] == len(pre) and segs["n_rows"] == sum(len(g) for g in pre)
+    assert segs["max_size"] == max([len(g) for g in pre] + [1 if n else 0])
+    for rnd in range(3):                                # the last level changes between rounds, the segments stay
+        codes[:, -1] = rng.integers(0, max(k // (rnd + 1), 2), size=n)
+        r = ops.collisions_in_segments(T(codes), segs)
+        if segs["max_size"] > 1024:
+            assert r["fallback"]
+            continue
+        assert not r["fallback"]
+        ref = ops.collisions(T(codes), [k] * L)
+        for key in ("n_unique", "n_groups", "n_rows", "max_multiplicity"):
+            assert r[key] == ref[key], key
+        def as_set(d):
+            off, mem = d["offsets"].cpu().numpy(), d["members"].cpu().numpy()
+            return sorted(tuple(mem[off[g]:off[g + 1]].tolist()) for g in range(d["n_groups"]))
+        assert as_set(r) == as_set(ref)
+        assert int(r["offsets"][-1]) == r["n_rows"]
+
+
 def test_sort_is_a_permutation_at_full_size():
     """Size-independent properties at 10M items: sortedness, permutation, unique count vs torch.unique."""
     n, k, L = 10_000_000, 256, 4
@@ -351,6 +381,37 @@ def test_generate_indices_end_to_end(golden, name, tmp_path):
     assert (codes_dev.numpy()[:, :3] != ref_final[:, :3]).any(axis=1).sum() <= 2
     G.write_index_json(codes_dev, str(tmp_path / "a.json"))
     assert (tmp_path / "a.json").read_text() == O.index_json(codes_dev.numpy())
+
+
+def test_segment_rounds_equal_global_sort_rounds():
+    """Whole generation with and without the prefix-segment shortcut gives identical codes and statistics."""
+    dims = [4096, 2048, 1024, 512, 256, 128, 64, 32]
+    ws, bs, cbs = seeded_weights(dims, [256] * 4, 32, seed=3, cb_scale=0.02)
+    x = T(synth_items(20000, 4096, n_parents=2500, seed=11))
+    m = RQVAE(in_dim=4096, num_emb_list=[256] * 4, e_dim=32, layers=dims[1:-1], sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50)
+    sd = m.state_dict()
+    lin = sorted([k for k in sd if k.startswith("encoder.mlp_layers.") and k.endswith(".weight")], key=lambda s: int(s.split(".")[2]))
+    for k, w, b in zip(lin, ws, bs):
+        sd[k] = torch.from_numpy(w); sd[k.replace(".weight", ".bias")] = torch.from_numpy(b)
+    for l, cb in enumerate(cbs):
+        sd[f"rq.vq_layers.{l}.embedding.weight"] = torch.from_numpy(cb)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    try:
+        ops.indexer_set_segments(False)
+        c0, s0 = G.generate_codes(m, x)
+        ops.indexer_set_segments(True)
+        c1, s1 = G.generate_codes(m, x)
+    finally:
+        ops.indexer_set_segments(True)
+    assert s0["rounds"] >= 2 and s0 == s1
+    assert torch.equal(c0, c1)
+    # the rounds alone on caller-owned tensors (the multi-GPU bucket path) reproduce the same table
+    ix = G.build_indexer(m, x.shape[0])
+    ix.pass0(x)
+    codes, resid = ix.codes_view(x.shape[0]).clone(), ix.resid_view(x.shape[0]).clone()
+    s2 = ix.resolve_device(codes, resid, 20)
+    assert torch.equal(codes.cpu(), c1.cpu()) and s2["n_unique"] == s1["n_unique"]
 
 
 def test_generate_indices_empty_and_unique_inputs(golden):
