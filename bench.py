@@ -9,7 +9,8 @@ quantisation -> up to 20 rounds of sort/unique + per-group Sinkhorn) over the wh
 Workload (BASELINE.json configs[2], the largest that fits one GPU): 1 M items x 4096-d fp32 per GPU,
 encoder 4096-2048-1024-512-256-128-64-32, 4 x 256 codes, e_dim 32, eps_last 0.003, 50 Sinkhorn
 iterations; for N > 1 every rank holds its own 1 M items (weak scaling, BASELINE.json configs[3] shape)
-and the ranks resolve collisions over the union (code all-gather + per-round delta all-reduce, NCCL).
+and the ranks resolve collisions over the union (one all-gather of codes + residuals, prefix-bucket ownership,
+one all-reduce of the final last-level codes; NCCL).
 Inputs (16.4 GB per GPU) are larger than the 126 MB L2, so no flush is needed between steps.
 One JSON line on stdout (rank 0).
 """
@@ -322,19 +323,29 @@ def run_gpu_arm(a):
         del xh
 
     if rank == 0:
-        # roofline of the dominant kernel: encoder layer 1 (4096 -> 2048), tcgen05 3xTF32
+        # roofline of the dominant kernel: encoder layer 1 (4096 -> 2048)
         l1_ms, l1_calls = prof.get(1, (0.0, 0))
         rows_per_launch = min(a.chunk_rows, n_local)
         flops_launch = 2.0 * DIMS[0] * DIMS[1] * (n_local * a.steps / max(l1_calls, 1))
         ach = flops_launch / (l1_ms / max(l1_calls, 1) * 1e-3) / 1e12 if l1_calls else None
         stage_ms = {str(k): round(v[0] / a.steps, 4) for k, v in sorted(prof.items())}
-        eng = "f16 x3, linear_split3_kernel<256,32,4,true>" if a.engine == 1 else "tf32 x3, linear_split3_kernel<256,16,4,false>"
+        eng = ("f16 x3, linear_pair_kernel<64,3> (tcgen05 cta_group::2, 256x256 tiles, persistent)" if a.engine == 1
+               else "tf32 x3, linear_split3_kernel<256,16,4,false>")
+        traffic = None
+        try:   # DRAM bytes of one launch of this kernel from the committed ncu --set full capture (same rows per launch)
+            summ = json.load(open(os.path.join(ROOT, "profiles", "r1_v5_pair_ncu_summary.json")))["layer1"]
+            if a.engine == 1 and summ["rows_per_launch"] == rows_per_launch:
+                traffic = summ["dram_bytes_read"] + summ["dram_bytes_write"]
+        except Exception:  # noqa: BLE001
+            traffic = None
         roof = {"bound": "tensor", "kernel": f"{eng} (encoder layer 1, 4096->2048)",
                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["bf16_sustained"]) if ach else None,
-                "traffic": None, "peak_source": pk["source"] + ", bf16 dense sustained",
+                "traffic": traffic, "traffic_unit": "bytes of DRAM read + write per launch (ncu, profiles/r1_v5_pair_ncu_summary.json); "
+                                                    "algorithmic: 2.18 GB operands + 1.07 GB output",
+                "peak_source": pk["source"] + ", bf16 dense sustained",
                 "note": "achieved = algorithmic fp32 GEMM FLOPs (2*M*4096*2048 per launch) / CUDA-event launch time; the kernel issues 3 MMAs "
                         "per product (fp32-accurate two-term operand split): tensor work = 3x achieved; ceiling = peak/3 with f16 operands "
-                        "(kind::f16 runs at the bf16 rate), peak/6 with tf32 operands",
+                        "(kind::f16 runs at the bf16 rate), peak/6 with tf32 operands.  ncu: tensor pipe 91 % active at the power-capped clock",
                 "tensor_work_tflops": 3 * ach if ach else None,
                 "frac_of_split_ceiling": (ach / (pk["bf16_sustained"] / (3 if a.engine == 1 else 6))) if ach else None,
                 "launches": l1_calls, "avg_launch_ms": l1_ms / max(l1_calls, 1), "rows_per_launch": rows_per_launch,
