@@ -114,6 +114,13 @@ int lcrec_center_distances(const float* d, int64_t n_rows, int n_codes, double* 
  * members[offsets[g] .. offsets[g+1]).  Writes new_code[item] for every member.
  * n_groups_dev: device int64 holding the group count (<= max_groups, the launch bound). */
 int64_t lcrec_sinkhorn_groups_workspace_bytes(int64_t max_rows, int n_codes);
+/* same, restricted to the groups g with g % part_mod == part_rem, and with an optional bound on the rows of the
+ * largest group (max_group_rows, 0 = unknown) that lets the library skip size classes that cannot occur */
+int lcrec_sinkhorn_groups_ex(const float* resid, int e_dim, const float* codebook, int n_codes,
+                             const int64_t* offsets, const int64_t* members, const int64_t* n_groups_dev,
+                             int64_t max_groups, int64_t max_rows, int64_t max_group_rows, double epsilon, int iters,
+                             int64_t* codes, int n_levels, int level, int part_mod, int part_rem, int32_t* flags,
+                             void* ws, int64_t ws_bytes, void* stream);
 int lcrec_sinkhorn_groups(const float* resid, int e_dim, const float* codebook, int n_codes,
                           const int64_t* offsets, const int64_t* members, const int64_t* n_groups_dev,
                           int64_t max_groups, int64_t max_rows, double epsilon, int iters,

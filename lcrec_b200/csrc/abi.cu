@@ -276,9 +276,9 @@ static int rounds_impl(lcrec_indexer_t* ix, int64_t* codes, const float* resid, 
     }
     {
       ProfScope prof(22, st);
-      LC_TRY(lcrec_sinkhorn_groups(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
-                                   ix->counts + 1, groups, rows, ix->eps, ix->iters, codes, ix->L, ix->L - 1,
-                                   ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));
+      LC_TRY(lcrec_sinkhorn_groups_ex(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
+                                      ix->counts + 1, groups, rows, c[3], ix->eps, ix->iters, codes, ix->L, ix->L - 1, 1, 0,
+                                      ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));
     }
     tot_rows += rows;
     ++rounds;
