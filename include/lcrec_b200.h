@@ -87,6 +87,10 @@ int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* 
 int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_levels, const float* const* codebooks,
                       const int32_t* n_codes, int n_levels_run, int resid_level, int64_t* codes,
                       float* xq, float* resid_last, double* sq_err, void* stream);
+/* Kernel choice of lcrec_rq_quantize: 0 = never the tensor-core distance path, 1 (default) = tensor cores (CTA-pair
+ * tcgen05 GEMM with a distance + argmin epilogue, fp32-accurate split operands) for large codebooks (>= 4096 codes or
+ * e_dim >= 128; code counts multiples of 256), 2 = whenever the shape allows it (cross-checks). */
+int lcrec_rq_set_tc_mode(int mode);
 
 /* ---- a4: distances only (index/models/vq.py:71-73), (n, K) fp32 ------------------------ */
 int lcrec_vq_distances(const float* r, int64_t n, int e_dim, const float* codebook, int n_codes,

@@ -45,6 +45,7 @@ SIGNATURES = {
                                         C.c_int, vp, vp, i64, vp]),
     "lcrec_sinkhorn_groups_part": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, f64, C.c_int, vp, C.c_int,
                                              C.c_int, C.c_int, C.c_int, vp, vp, i64, vp]),
+    "lcrec_rq_set_tc_mode": (C.c_int, [C.c_int]),
     "lcrec_sinkhorn_groups_ex": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, i64, f64, C.c_int, vp, C.c_int,
                                            C.c_int, C.c_int, C.c_int, vp, vp, i64, vp]),
     "lcrec_sinkhorn_set_mode": (C.c_int, [C.c_int]),

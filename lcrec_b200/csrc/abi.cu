@@ -166,7 +166,7 @@ extern "C" int lcrec_indexer_create(lcrec_mlp_t* encoder, int e_dim, int n_level
   ix->chunk_rows = std::min(chunk_rows, max_items);
   IX_ALLOC(ix->codes, sizeof(int64_t) * max_items * n_levels);
   IX_ALLOC(ix->resid, sizeof(float) * max_items * e_dim);
-  IX_ALLOC(ix->z, sizeof(float) * ix->chunk_rows * e_dim);
+  IX_ALLOC(ix->z, sizeof(float) * max_items * e_dim);      // latents of all rows of one pass0 call: ONE fused RQ launch
   ix->mlp_ws_bytes = lcrec_mlp_workspace_bytes(encoder, ix->chunk_rows);
   IX_ALLOC(ix->mlp_ws, ix->mlp_ws_bytes);
   IX_ALLOC(ix->offsets, sizeof(int64_t) * (max_items + 1));
@@ -212,10 +212,12 @@ extern "C" int lcrec_indexer_pass0(lcrec_indexer_t* ix, const float* x, int64_t 
   LC_ARG(x != nullptr);
   for (int64_t s = 0; s < n; s += ix->chunk_rows) {
     const int64_t m = std::min(ix->chunk_rows, n - s);
-    LC_TRY(lcrec_mlp_forward(ix->enc, x + s * ix->in_dim, m, ix->z, nullptr, ix->mlp_ws, ix->mlp_ws_bytes, stream));
+    LC_TRY(lcrec_mlp_forward(ix->enc, x + s * ix->in_dim, m, ix->z + s * ix->D, nullptr, ix->mlp_ws, ix->mlp_ws_bytes, stream));
+  }
+  {
     ProfScope prof(20, (cudaStream_t)stream);
-    LC_TRY(lcrec_rq_quantize(ix->z, m, ix->D, ix->L, ix->cb.data(), ix->K.data(), ix->L, ix->L - 1,
-                             ix->codes + (row_offset + s) * ix->L, nullptr, ix->resid + (row_offset + s) * ix->D,
+    LC_TRY(lcrec_rq_quantize(ix->z, n, ix->D, ix->L, ix->cb.data(), ix->K.data(), ix->L, ix->L - 1,
+                             ix->codes + row_offset * ix->L, nullptr, ix->resid + row_offset * ix->D,
                              nullptr, stream));
   }
   return LCREC_OK;

@@ -30,11 +30,15 @@ struct PairProblem {
   __half *o_hi, *o_lo; int64_t ldo; float* o_inv_scale; int64_t ld_oscale;   // group-scaled output (group 256) or null
   int debug;
   void* trace = nullptr;        // measurement only (see linear_pair.cu)
+  // distance + argmin mode (launch_argmin_pair): squared norms of the rows / codes, output codes (stride in elements)
+  const float* xx = nullptr; const float* cc = nullptr; int64_t* codes = nullptr; int64_t codes_stride = 0;
 };
 
 // Linear(+bias)(+ReLU) on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, persistent).  n_out % 256 == 0.
 int launch_linear_pair(const PairProblem& p, cudaStream_t st);
 bool linear_pair_supported(int k, int n_out, int group);
+int launch_argmin_pair(const PairProblem& p, cudaStream_t st);
+bool argmin_pair_supported(int k, int n_out);
 constexpr int kPairGroup = 256;
 
 // x (rows, k) fp32 -> group-scaled fp16 hi/lo (one pass; scale groups of 256 elements)

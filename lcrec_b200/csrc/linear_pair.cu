@@ -44,6 +44,8 @@ struct PairArgs {
   const float* w_inv_scale; const float* bias; int relu;
   float* y; int64_t ldy;
   __half* o_hi; __half* o_lo; int64_t ldo; float* o_inv_scale; int64_t ld_oscale;
+  // ARGMIN mode (distance GEMM of the residual quantiser): d = (xx[row] + cc[col]) - 2 dot, first argmin over all n_out columns
+  const float* xx; const float* cc; int64_t* codes; int64_t codes_stride;
   int debug;
   long long* trace;   // measurement only: clock64 stamps of cluster 0's leader CTA (6 roles x 512 events x 4)
 };
@@ -67,7 +69,7 @@ __device__ __forceinline__ void stamp(long long* trace, int role, uint32_t idx, 
   if (trace != nullptr && idx < 512u) trace[((size_t)role * 512 + idx) * 4 + slot] = clock64();
 }
 
-template <int BK, int STAGES>
+template <int BK, int STAGES, bool ARGMIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
@@ -94,6 +96,10 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
   const int nkb = (args.k + BK - 1) / BK;
   const int nchunks = (nkb + C::KB_PER_CHUNK - 1) / C::KB_PER_CHUNK;
   long long* const trace = (blockIdx.x == 0) ? args.trace : nullptr;
+  // work units: one 256 x 256 tile (linear mode, n fastest) or one 256-row block with ALL its column tiles (ARGMIN mode:
+  // the running minimum of a row stays in the registers of the thread that owns it)
+  const int inner = ARGMIN ? args.tiles_n : 1;
+  const int64_t n_units = ARGMIN ? args.n_tiles / args.tiles_n : args.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -117,9 +123,10 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = cluster_id; tile < args.n_tiles; tile += n_clusters) {
-        const int tile_n = (int)(tile % args.tiles_n);
-        const int64_t tile_m = tile / args.tiles_n;
+      for (int64_t unit = cluster_id; unit < n_units; unit += n_clusters)
+      for (int nn = 0; nn < inner; ++nn) {
+        const int tile_n = ARGMIN ? nn : (int)(unit % args.tiles_n);
+        const int64_t tile_m = ARGMIN ? unit : unit / args.tiles_n;
         const int row0 = (int)(tile_m * 256 + rank * kHalfM);
         const int col0 = tile_n * kTileN + (int)rank * kHalfM;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -149,7 +156,8 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     if (rank == 0 && lane == 0) {
       constexpr uint32_t idesc = umma_idesc(256, kTileN, 0);
       uint32_t it = 0, cc = 0;
-      for (int64_t tile = cluster_id; tile < args.n_tiles; tile += n_clusters) {
+      for (int64_t unit = cluster_id; unit < n_units; unit += n_clusters)
+      for (int nn = 0; nn < inner; ++nn) {
         int kb = 0;
         for (int c = 0; c < nchunks; ++c, ++cc) {
           const uint32_t b = cc & 1u;
@@ -201,9 +209,11 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     uint32_t* stg = reinterpret_cast<uint32_t*>(smem + STAGES * C::STAGE_BYTES + 256) + warp * kStageWords;
     float* xch = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES + 256 + 8 * kStageWords * 4);   // 2 x 128 maxima
     uint32_t cc = 0, tcount = 0;
-    for (int64_t tile = cluster_id; tile < args.n_tiles; tile += n_clusters, ++tcount) {
-      const int tile_n = (int)(tile % args.tiles_n);
-      const int64_t tile_m = tile / args.tiles_n;
+    float run_best = INFINITY; int run_idx = 0;            // ARGMIN: running minimum of this thread's row and column half
+    for (int64_t unit = cluster_id; unit < n_units; unit += n_clusters)
+    for (int nn = 0; nn < inner; ++nn, ++tcount) {
+      const int tile_n = ARGMIN ? nn : (int)(unit % args.tiles_n);
+      const int64_t tile_m = ARGMIN ? unit : unit / args.tiles_n;
       const int64_t row = tile_m * 256 + rank * kHalfM + q * 32 + lane;
       const bool row_ok = row < args.n_rows;
       const float* sc_ptr = args.a_inv_scale + (row_ok ? row : 0);
@@ -233,8 +243,39 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         if (lane == 0) mbar_arrive_cluster(tempty_leader[b]);
         if (warp == 0 && lane == 0) stamp(trace, 3, cc, 2);
       }
-      // ---- epilogue from registers: 1/s_col, bias, ReLU; fp32 and / or the next layer's group-scaled fp16 pair
       const int col_base = tile_n * kTileN + half * NCOL;
+      if constexpr (ARGMIN) {
+        // ---- distance + first-argmin epilogue (vq.py:71-75): d = (|r|^2 + |c|^2) - 2 r.c in fp32, strict < keeps the lowest
+        // index inside the thread's ascending column scan; the two column halves of a row are merged at the end
+        if (nn == 0) { run_best = INFINITY; run_idx = 0; }
+        const float xr = __ldg(args.xx + (row_ok ? row : 0));
+#pragma unroll
+        for (int j = 0; j < NCOL; j += 4) {
+          const float4 cs = __ldg(reinterpret_cast<const float4*>(args.w_inv_scale + col_base + j));
+          const float4 cn = __ldg(reinterpret_cast<const float4*>(args.cc + col_base + j));
+          const float d0 = (xr + cn.x) - 2.f * (acc[j] * cs.x), d1 = (xr + cn.y) - 2.f * (acc[j + 1] * cs.y);
+          const float d2 = (xr + cn.z) - 2.f * (acc[j + 2] * cs.z), d3 = (xr + cn.w) - 2.f * (acc[j + 3] * cs.w);
+          if (d0 < run_best) { run_best = d0; run_idx = col_base + j; }
+          if (d1 < run_best) { run_best = d1; run_idx = col_base + j + 1; }
+          if (d2 < run_best) { run_best = d2; run_idx = col_base + j + 2; }
+          if (d3 < run_best) { run_best = d3; run_idx = col_base + j + 3; }
+        }
+        if (nn == inner - 1) {
+          float* xb = xch;                                           // 2 x 128 best values
+          int* xi = reinterpret_cast<int*>(stg);                     // this warp's staging words: 32 indices
+          if (half == 1) { xb[kHalfM + q * 32 + lane] = run_best; xi[lane] = run_idx; }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0) {
+            const float ob = xb[kHalfM + q * 32 + lane];
+            const int oi = reinterpret_cast<const int*>(stg + 4 * kStageWords)[lane];     // warp + 4 owns the other half
+            if (ob < run_best || (ob == run_best && oi < run_idx)) { run_best = ob; run_idx = oi; }
+            if (row_ok) args.codes[row * args.codes_stride] = (int64_t)run_idx;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        continue;
+      }
+      // ---- epilogue from registers: 1/s_col, bias, ReLU; fp32 and / or the next layer's group-scaled fp16 pair
       if (warp == 0 && lane == 0) stamp(trace, 4, tcount, 0);
       float amax = 0.f;
 #pragma unroll
@@ -404,10 +445,10 @@ __global__ void __launch_bounds__(256) split_groups_kernel(const float* __restri
   }
 }
 
-template <int BK, int STAGES>
+template <int BK, int STAGES, bool ARGMIN>
 int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
   using C = PairCfg<BK, STAGES>;
-  auto kern = linear_pair_kernel<BK, STAGES>;
+  auto kern = linear_pair_kernel<BK, STAGES, ARGMIN>;
   static bool attr_set = false;
   static int max_clusters = 0;
   if (!attr_set) {
@@ -436,7 +477,8 @@ int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
   a.y = p.y; a.ldy = p.ldy;
   a.o_hi = p.o_hi; a.o_lo = p.o_lo; a.ldo = p.ldo; a.o_inv_scale = p.o_inv_scale; a.ld_oscale = p.ld_oscale;
   a.debug = p.debug; a.trace = (long long*)p.trace;
-  const int64_t clusters = std::min<int64_t>(a.n_tiles, max_clusters);
+  a.xx = p.xx; a.cc = p.cc; a.codes = p.codes; a.codes_stride = p.codes_stride;
+  const int64_t clusters = std::min<int64_t>(ARGMIN ? a.n_tiles / a.tiles_n : a.n_tiles, max_clusters);
   kern<<<(unsigned)(2 * clusters), kPairThreads, C::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
   LC_LAUNCH_CHECK("linear_pair_kernel");
   return LCREC_OK;
@@ -447,6 +489,7 @@ int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
 bool linear_pair_supported(int k, int n_out, int group) {
   return group == kGroup && n_out >= kTileN && n_out % kTileN == 0 && k >= 64 && k % 8 == 0;
 }
+bool argmin_pair_supported(int k, int n_out) { return n_out >= kTileN && n_out % kTileN == 0 && k >= 8 && k % 8 == 0; }
 
 int launch_linear_pair(const PairProblem& p, cudaStream_t st) {
   if (p.n_rows == 0) return LCREC_OK;
@@ -459,8 +502,22 @@ int launch_linear_pair(const PairProblem& p, cudaStream_t st) {
     set_error("linear_pair: bias / channel scales must be 16-byte aligned");
     return LCREC_ERR_ARG;
   }
-  if (p.debug & 4) return launch_pair_cfg<32, 6>(p, st);
-  return launch_pair_cfg<64, 3>(p, st);
+  if (p.debug & 4) return launch_pair_cfg<32, 6, false>(p, st);
+  return launch_pair_cfg<64, 3, false>(p, st);
+}
+
+// codes[row * codes_stride] = first argmin over the n_out codes of (xx[row] + cc[code]) - 2 <a_row, w_code>
+int launch_argmin_pair(const PairProblem& p, cudaStream_t st) {
+  if (p.n_rows == 0) return LCREC_OK;
+  if (!argmin_pair_supported(p.k, p.n_out) || p.a.group != kGroup || !p.xx || !p.cc || !p.codes) {
+    set_error("argmin_pair: unsupported problem k=%d n_out=%d", p.k, p.n_out);
+    return LCREC_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(p.w_inv_scale) & 15) || (reinterpret_cast<uintptr_t>(p.cc) & 15)) {
+    set_error("argmin_pair: code norms / scales must be 16-byte aligned");
+    return LCREC_ERR_ARG;
+  }
+  return launch_pair_cfg<64, 3, true>(p, st);
 }
 
 int launch_split_groups(const float* x, int64_t rows, int k, int64_t ldx, __half* hi, __half* lo, int64_t ld_out,

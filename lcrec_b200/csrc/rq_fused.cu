@@ -10,7 +10,10 @@
 // all levels (4 x 256 x 32 fp32 = 128 KB at the run.sh shape) and their squared norms are staged
 // once per CTA in shared memory and read as warp-wide broadcasts.  The kernel is FP32-FMA bound
 // (65 536 FLOP per 128 B read), not HBM bound.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "linear.cuh"
 
 namespace lcrec {
 
@@ -270,6 +273,128 @@ __global__ void vq_distances_kernel(const float* __restrict__ r, int64_t n, int 
   }
 }
 
+// ---------------------------------------------------------------------------- tensor-core path (large codebooks)
+// Level step of the tensor-core residual quantiser: apply the codes of the previous level (x_res = r + (q - r),
+// r -= x_res, x_q += x_res, squared error; vq.py:87-95 / rq.py:47-48), then prepare the operand of the next distance
+// GEMM: |r|^2 (sequential fma chain, the order of the other kernels), fp16 hi/lo with one power-of-two scale per
+// (row, 256 columns).  One warp per row, the row lives in shared memory.
+struct RqTcPrep {
+  const float* src; float* r; int64_t n; int D;
+  const int64_t* codes; int64_t codes_stride; const float* cb_prev;     // null on the first level
+  float* xq; int xq_first; double* sq_err; float* resid_out;
+  __half* hi; __half* lo; int64_t ld_out; float* inv_scale; int64_t ld_scale; float* xx;    // hi == null: apply only
+};
+__global__ void __launch_bounds__(256) rq_tc_prepare_kernel(const RqTcPrep a) {
+  extern __shared__ float sm[];
+  __shared__ double red[8];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* row = sm + (size_t)warp * a.D;
+  double err = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)warps + warp; i < a.n; i += (int64_t)gridDim.x * warps) {
+    const int64_t code = a.cb_prev ? a.codes[i * a.codes_stride] : 0;
+    for (int d = lane; d < a.D; d += 32) {
+      float v = a.src[i * a.D + d];
+      if (a.cb_prev) {
+        const float t = __ldg(a.cb_prev + code * a.D + d) - v;
+        err += (double)(t * t);
+        const float xres = v + t;
+        v = v - xres;
+        if (a.xq) a.xq[i * a.D + d] = a.xq_first ? xres : a.xq[i * a.D + d] + xres;
+      }
+      row[d] = v;
+      if (a.r) a.r[i * a.D + d] = v;
+      if (a.resid_out) a.resid_out[i * a.D + d] = v;
+    }
+    __syncwarp();
+    if (a.hi != nullptr) {
+      float xx = 0.f;
+      for (int d = 0; d < a.D; ++d) xx = fmaf(row[d], row[d], xx);      // every lane runs the same chain
+      if (lane == 0) a.xx[i] = xx;
+      for (int g0 = 0; g0 < a.ld_out; g0 += 256) {
+        float m = 0.f;
+        for (int d = g0 + lane; d < min(g0 + 256, a.D); d += 32) m = fmaxf(m, fabsf(row[d]));
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 1.f, is = 1.f;
+        if (m > 0.f && m < INFINITY) {
+          int e;
+          frexpf(m, &e);
+          const int sh = min(max(15 - e, -100), 100);
+          s = ldexpf(1.f, sh); is = ldexpf(1.f, -sh);
+        }
+        if (lane == 0) a.inv_scale[(int64_t)(g0 >> 8) * a.ld_scale + i] = is;
+        for (int d = g0 + lane; d < min((int64_t)g0 + 256, a.ld_out); d += 32) {
+          const float xs = (d < a.D ? row[d] : 0.f) * s;
+          const __half h = __float2half_rn(xs);
+          a.hi[i * a.ld_out + d] = h;
+          a.lo[i * a.ld_out + d] = __float2half_rn(xs - __half2float(h));
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (a.sq_err) {
+    const double t = block_sum_double(err, red);
+    if (threadIdx.x == 0) atomicAdd(a.sq_err, t);
+  }
+}
+
+int launch_split_f16(const float* x, int64_t rows, int k, int64_t ldx, __half* hi, __half* lo, int64_t ld_out,
+                     float* inv_scale, cudaStream_t st);                      // linear_tf32x3.cu
+__global__ void code_norms_kernel(const float* __restrict__ cb, int k, int D, float* __restrict__ out);
+
+// All levels on the tensor cores: per level {prepare, distance GEMM + argmin on CTA pairs (launch_argmin_pair)}.
+// Used for codebooks that do not fit the shared-memory kernel (>= 4096 codes or e_dim >= 128, e.g. 4 x 8192 x 256).
+static int rq_quantize_tc(const RqArgs& a, int D, cudaStream_t st) {
+  const int64_t n = a.n;
+  const int64_t ldh = round_up(D, 8);
+  const int64_t groups = ceil_div(ldh, 256);
+  int kmax = 0;
+  for (int l = 0; l < a.n_levels_run; ++l) kmax = std::max(kmax, a.k[l]);
+  const size_t bytes_r = sizeof(float) * n * D, bytes_h = sizeof(__half) * n * ldh, bytes_s = sizeof(float) * n * groups,
+               bytes_x = sizeof(float) * n, bytes_wh = sizeof(__half) * (size_t)kmax * ldh, bytes_ws = sizeof(float) * kmax;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t total = al(bytes_r) + 2 * al(bytes_h) + al(bytes_s) + al(bytes_x) + 2 * al(bytes_wh) + 2 * al(bytes_ws) + 256;
+  char* ws = nullptr;
+  LC_CUDA(cudaMallocAsync((void**)&ws, total, st));
+  char* p = ws;
+  auto take = [&](size_t b) { char* q = p; p += al(b); return q; };
+  float* r = (float*)take(bytes_r);
+  __half* hi = (__half*)take(bytes_h); __half* lo = (__half*)take(bytes_h);
+  float* sc = (float*)take(bytes_s); float* xx = (float*)take(bytes_x);
+  __half* w_hi = (__half*)take(bytes_wh); __half* w_lo = (__half*)take(bytes_wh);
+  float* w_sc = (float*)take(bytes_ws); float* cc = (float*)take(bytes_ws);
+  const int warps = 8;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, warps), (int64_t)num_sms() * 8);
+  const size_t smem = sizeof(float) * warps * D;
+  int rc = LCREC_OK;
+  auto run = [&]() -> int {
+    for (int l = 0; l <= a.n_levels_run; ++l) {
+      const bool last = l == a.n_levels_run;
+      if (last && !(a.xq || a.sq_err || (a.resid_last && a.resid_level >= a.n_levels_run))) break;
+      RqTcPrep q{};
+      q.src = l == 0 ? a.z : r; q.r = r; q.n = n; q.D = D;
+      if (l > 0) { q.codes = a.codes + (l - 1); q.codes_stride = a.n_levels; q.cb_prev = a.cb[l - 1]; q.xq = a.xq; q.xq_first = l == 1; q.sq_err = a.sq_err ? a.sq_err + (l - 1) : nullptr; }
+      q.resid_out = (a.resid_last && (l == a.resid_level || (last && a.resid_level >= a.n_levels_run))) ? a.resid_last : nullptr;
+      if (!last) { q.hi = hi; q.lo = lo; q.ld_out = ldh; q.inv_scale = sc; q.ld_scale = n; q.xx = xx; }
+      rq_tc_prepare_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(q);
+      LC_LAUNCH_CHECK("rq_tc_prepare_kernel");
+      if (last) break;
+      LC_TRY(launch_split_f16(a.cb[l], a.k[l], D, D, w_hi, w_lo, ldh, w_sc, st));
+      code_norms_kernel<<<(unsigned)ceil_div(a.k[l], 256), 256, 0, st>>>(a.cb[l], a.k[l], D, cc);
+      LC_LAUNCH_CHECK("code_norms_kernel");
+      PairProblem pp{};
+      pp.a.hi = hi; pp.a.lo = lo; pp.a.ld = ldh; pp.a.inv_scale = sc; pp.a.ld_scale = n; pp.a.group = kPairGroup;
+      pp.n_rows = n; pp.k = D; pp.w_hi = w_hi; pp.w_lo = w_lo; pp.ldw = ldh; pp.w_inv_scale = w_sc; pp.n_out = a.k[l];
+      pp.xx = xx; pp.cc = cc; pp.codes = a.codes + l; pp.codes_stride = a.n_levels;
+      LC_TRY(launch_argmin_pair(pp, st));
+    }
+    return LCREC_OK;
+  };
+  rc = run();
+  (void)cudaFreeAsync(ws, st);
+  return rc;
+}
+
 template <int D, int IPT, bool TRAIN>
 static int launch_rq_smem_impl(const RqArgs& a, size_t smem, cudaStream_t st) {
   static bool attr = false;
@@ -291,6 +416,15 @@ static int launch_rq_smem(const RqArgs& a, size_t smem, cudaStream_t st) {
 }  // namespace lcrec
 
 using namespace lcrec;
+
+static int g_rq_tc_mode = 1;
+// 0 = never use the tensor-core distance path, 1 (default) = for large codebooks (>= 4096 codes or e_dim >= 128),
+// 2 = whenever the shape allows it (cross-checks)
+extern "C" int lcrec_rq_set_tc_mode(int mode) {
+  LC_ARG(mode >= 0 && mode <= 2);
+  g_rq_tc_mode = mode;
+  return LCREC_OK;
+}
 
 extern "C" int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_levels, const float* const* codebooks,
                                  const int32_t* n_codes, int n_levels_run, int resid_level, int64_t* codes,
@@ -314,11 +448,16 @@ extern "C" int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_lev
                        (!resid_last || (reinterpret_cast<uintptr_t>(resid_last) & 15) == 0);
   bool cb_aligned = true;
   for (int l = 0; l < n_levels_run; ++l) cb_aligned = cb_aligned && (reinterpret_cast<uintptr_t>(codebooks[l]) & 15) == 0;
+  // tensor-core distance path (CTA-pair GEMM + argmin epilogue) for the shapes it serves
+  bool tc_ok = codes != nullptr && n_levels_run > 0 && g_rq_tc_mode != 0 && n >= 1024, tc_big = false;
+  for (int l = 0; l < n_levels_run; ++l) { tc_ok = tc_ok && argmin_pair_supported(e_dim, n_codes[l]); tc_big = tc_big || n_codes[l] >= 4096; }
+  if (tc_ok && g_rq_tc_mode == 2) return rq_quantize_tc(a, e_dim, st);
   if (smem <= 200 * 1024 && aligned && cb_aligned && n_levels_run > 0) {
     if (e_dim == 32) return launch_rq_smem<32>(a, smem, st);
     if (e_dim == 16) return launch_rq_smem<16>(a, smem, st);
     if (e_dim == 64) return launch_rq_smem<64>(a, smem, st);
   }
+  if (tc_ok && (tc_big || e_dim >= 128)) return rq_quantize_tc(a, e_dim, st);
   // generic path
   float* norms = nullptr;
   LC_CUDA(cudaMallocAsync(&norms, sizeof(float) * std::max<int64_t>(total_codes, 1), st));

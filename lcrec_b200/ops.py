@@ -162,6 +162,11 @@ def linear_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], 
 
 
 # --------------------------------------------------------------------------- RQ
+def rq_set_tc_mode(mode: int) -> None:
+    """0 = SIMT kernels only, 1 = tensor-core distance GEMM for large codebooks (default), 2 = whenever possible."""
+    _lib.check(_lib.load().lcrec_rq_set_tc_mode(int(mode)))
+
+
 def rq_quantize(z: torch.Tensor, codebooks: Sequence[torch.Tensor], n_levels_run: Optional[int] = None,
                 resid_level: int = -1, want_codes: bool = True, want_xq: bool = False,
                 want_sq_err: bool = False):

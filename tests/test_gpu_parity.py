@@ -121,6 +121,46 @@ def test_rq_fused_matches_oracle(n, d, ks):
     np.testing.assert_allclose(loss, loss_o, rtol=1e-5)
 
 
+@pytest.mark.parametrize("n,d,ks,force", [(3000, 256, [8192, 8192], False), (5000, 128, [512, 256, 256], False),
+                                          (6000, 32, [256] * 4, True), (2500, 64, [4096, 256], True), (1500, 40, [256, 512], True)])
+def test_rq_tensor_core_path_matches_oracle(n, d, ks, force):
+    """Large-codebook variant (BASELINE configs[4]: 8192 codes x 256 dims): distance GEMM + argmin on the tensor cores
+    (CTA-pair tcgen05 kernel, fp32-accurate split operands).  Codes equal the oracle's apart from counted near-ties;
+    forced onto the small shapes it equals the SIMT kernel the same way."""
+    rng = np.random.default_rng(n + d)
+    z = rng.standard_normal((n, d)).astype(np.float32)
+    z[7] = z[3]
+    cbs = [(rng.standard_normal((k, d)) * 0.7 * 0.6 ** l).astype(np.float32) for l, k in enumerate(ks)]
+    cbs[0][5] = cbs[0][2]                             # exact tie between two codes: lowest index wins
+    p = O.RqvaeParams(encoder=None, codebooks=cbs, sk_epsilons=[0.0] * len(ks))
+    try:
+        ops.rq_set_tc_mode(2 if force else 1)
+        r = ops.rq_quantize(T(z), [T(c) for c in cbs], resid_level=len(ks) - 1, want_xq=True, want_sq_err=True)
+    finally:
+        ops.rq_set_tc_mode(1)
+    codes = r["codes"].cpu().numpy()
+    xq_o, loss_o, codes_o = O.rq_forward(z, p, use_sk=False)
+    near, hard = O.classify_code_mismatches(z, p, codes)
+    assert hard == 0 and near <= max(3, n // 500)
+    same = (codes == codes_o).all(axis=1)
+    assert (~same).sum() <= near
+    assert (codes[7] == codes[3]).all() and not (codes[:, 0] == 5).any()
+    np.testing.assert_allclose(r["xq"].cpu().numpy()[same], xq_o[same], rtol=1e-5, atol=1e-6)
+    resids, _, _ = O.rq_trace(z, p)
+    np.testing.assert_allclose(r["resid"].cpu().numpy()[same], resids[-1][same], rtol=1e-5, atol=1e-6)
+    if same.all():
+        mse = r["sq_err"].cpu().numpy() / (n * d)
+        loss = np.mean([(m + p.beta * m) for m in mse.astype(np.float32)])
+        np.testing.assert_allclose(loss, loss_o, rtol=1e-5)
+    ops.rq_set_tc_mode(0)
+    try:
+        r0 = ops.rq_quantize(T(z), [T(c) for c in cbs])
+    finally:
+        ops.rq_set_tc_mode(1)
+    diff = (r0["codes"].cpu().numpy() != codes).any(axis=1)
+    assert diff.sum() <= near + max(3, n // 500)      # SIMT path vs tensor-core path: near-ties only
+
+
 def test_vq_distances_match_oracle():
     rng = np.random.default_rng(0)
     r = rng.standard_normal((300, 32)).astype(np.float32)
