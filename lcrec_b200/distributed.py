@@ -7,12 +7,12 @@ The reference's index/ directory is single-process; this is the north-star shard
   replicated, no communication (the 16 KB/item embeddings never leave their rank);
 * collision detection needs a global view, but two items can only ever collide if they share the
   first L-1 codes (the rounds rewrite the LAST level only, generate_indices.py:101-105), so the
-  global problem splits into independent PREFIX BUCKETS.  After PASS 0 the codes (32 B/item) and
-  the residuals entering the last level (128 B/item) are all-gathered once; rank r then owns the
-  buckets with ``prefix % world == r``, runs the whole <=20-round loop on them locally (1/world of
-  the sort and Sinkhorn work, no per-round communication), and one all-reduce of the last-level
-  codes (8 B/item) returns the results.  Groups, member order and arithmetic are exactly those of
-  the single-GPU run, so the result is identical bit for bit.
+  global problem splits into independent PREFIX BUCKETS.  After PASS 0 every item's codes (32 B)
+  and residual entering the last level (128 B) travel ONCE, by all-to-all, to the rank that owns its
+  bucket (``hash(prefix) % world``); the owner runs the whole <=20-round loop on its buckets locally
+  (1/world of the sort and Sinkhorn work, no per-round communication) and a second all-to-all along
+  the same routes returns the last-level codes (8 B/item).  Groups, member order and arithmetic are
+  exactly those of the single-GPU run, so the result is identical bit for bit.
 
 The arithmetic lives behind a small backend interface so that the host logic above can be
 exercised with ``gloo`` on CPU in the tests (where the backend is the numpy oracle); the product
@@ -71,7 +71,8 @@ class CudaBackend:
         from . import ops
         self.ops = ops
         self.model = model
-        self.indexer = G.build_indexer(model, max(n_local_max, 1), min(chunk_rows, max(n_local_max, 1)))
+        # 5 % slack: the hash-balanced bucket share of a rank may slightly exceed its item share
+        self.indexer = G.build_indexer(model, int(max(n_local_max, 1) * 1.05) + 1024, min(chunk_rows, max(n_local_max, 1)))
         self.cbs = [vq.embedding.weight.detach() for vq in model.rq.vq_layers]
         self.n_codes = [int(c.shape[0]) for c in self.cbs]
         self.eps = float(model.rq.vq_layers[-1].sk_epsilon)
@@ -147,26 +148,36 @@ def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank
         stats = resolve_rounds(backend, codes, resid_local, max_rounds)
         stats["collision_rate"] = (plan.n_total - stats["n_unique"]) / max(plan.n_total, 1)
         return codes, stats
-    codes_all = all_gather_rows(codes_local, plan, rank, group)
-    resid_all = all_gather_rows(resid_local, plan, rank, group)
-    mine = torch.nonzero(bucket_owner(codes_all, n_codes, plan.world) == rank).squeeze(1)   # ascending item ids
-    sub_codes = codes_all.index_select(0, mine).contiguous()
-    sub_resid = resid_all.index_select(0, mine).contiguous()
+    # Every rank sends each item to the owner of its prefix bucket (all-to-all: 160 B/item leave the rank once, instead
+    # of every rank gathering all items).  Items arrive grouped by source rank = ascending global item id, because the
+    # shards are contiguous blocks and the send order inside a shard is ascending.
+    world = plan.world
+    last = codes_local.shape[1] - 1
+    owner = bucket_owner(codes_local, n_codes, world)
+    order = torch.argsort(owner, stable=True)                      # items grouped by destination, ascending inside
+    send_counts = torch.bincount(owner, minlength=world)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    send_splits, recv_splits = send_counts.tolist(), recv_counts.tolist()
+    n_mine = int(sum(recv_splits))
+    sub_codes = torch.empty((n_mine, codes_local.shape[1]), dtype=codes_local.dtype, device=codes_local.device)
+    sub_resid = torch.empty((n_mine, resid_local.shape[1]), dtype=resid_local.dtype, device=resid_local.device)
+    dist.all_to_all_single(sub_codes, codes_local.index_select(0, order).contiguous(), recv_splits, send_splits, group=group)
+    dist.all_to_all_single(sub_resid, resid_local.index_select(0, order).contiguous(), recv_splits, send_splits, group=group)
     st = resolve_rounds(backend, sub_codes, sub_resid, max_rounds)
-    last = codes_all.shape[1] - 1
-    final_last = torch.zeros(plan.n_total, dtype=torch.int64, device=codes_all.device)
-    final_last[mine] = sub_codes[:, last]
+    # the owners return the resolved last-level codes along the same routes
+    back = torch.empty((codes_local.shape[0],), dtype=codes_local.dtype, device=codes_local.device)
+    dist.all_to_all_single(back, sub_codes[:, last].contiguous(), send_splits, recv_splits, group=group)
+    out = codes_local.clone()
+    out[order, last] = back
     agg = torch.tensor([st["n_unique"], st["groups_round1"], st["rows_round1"], st["sinkhorn_rows"]], dtype=torch.int64,
-                       device=codes_all.device)
-    mx = torch.tensor([st["rounds"], st["max_multiplicity"]], dtype=torch.int64, device=codes_all.device)
-    dist.all_reduce(final_last, op=dist.ReduceOp.SUM, group=group)       # buckets are disjoint: a sum is a scatter
+                       device=codes_local.device)
+    mx = torch.tensor([st["rounds"], st["max_multiplicity"]], dtype=torch.int64, device=codes_local.device)
     dist.all_reduce(agg, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    out = codes_local.clone()
-    out[:, last] = final_last[plan.slice(rank)]
     n_unique, g1, r1, rows = [int(v) for v in agg.tolist()]
     rounds, max_mult = [int(v) for v in mx.tolist()]
     stats = {"rounds": rounds, "n_unique": n_unique, "groups_round1": g1, "rows_round1": r1, "sinkhorn_rows": rows,
              "max_multiplicity": max_mult, "collision_rate": (plan.n_total - n_unique) / max(plan.n_total, 1),
-             "bucket_items_this_rank": int(mine.numel())}
+             "bucket_items_this_rank": n_mine}
     return out, stats
