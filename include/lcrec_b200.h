@@ -109,6 +109,17 @@ int lcrec_sinkhorn_dense(const double* distances, int64_t n_rows, int n_codes, d
                          int64_t ws_bytes, void* stream);
 /* center_distance_for_constraint (vq.py:51-61): fp32 in, centred fp64 out (the .double() of
  * vq.py:78).  status (1 int32, device): set to 1 when amplitude <= 0. */
+/* sinkhorn_algorithm (layers.py:85-108) on ONE (n_rows_global x n_codes) problem whose rows are split over the ranks
+ * of a data-parallel job (the DP form of the training step, trainer.py:114): row steps are local, the initial total
+ * and the per-iteration column marginals are summed inside the kernel through peer memory (NVLink P2P on symmetric
+ * buffers, rank-ordered sum => identical marginals on all ranks).  peers_dev: device array of `world` pointers to the
+ * ranks' symmetric buffers (lcrec_sinkhorn_dist_symmetric_bytes each, zeroed once); epoch must grow by >= iters + 2
+ * per call.  Collective: every rank calls it with its own rows.  Workspace as lcrec_sinkhorn_workspace_bytes. */
+int64_t lcrec_sinkhorn_dist_symmetric_bytes(int n_codes);
+int lcrec_sinkhorn_dense_dist(const double* distances, int64_t n_rows_local, int64_t n_rows_global, int n_codes,
+                              double epsilon, int iters, double* q, int64_t* argmax, int32_t* flags,
+                              void* const* peers_dev, int world, int rank, uint64_t epoch, void* ws, int64_t ws_bytes,
+                              void* stream);
 int lcrec_center_distances(const float* d, int64_t n_rows, int n_codes, double* centred,
                            int32_t* status, void* ws, int64_t ws_bytes, void* stream);
 

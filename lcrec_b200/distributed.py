@@ -181,3 +181,62 @@ def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank
              "max_multiplicity": max_mult, "collision_rate": (plan.n_total - n_unique) / max(plan.n_total, 1),
              "bucket_items_this_rank": n_mine}
     return out, stats
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Data-parallel form of the training-time Sinkhorn (one (global batch x K) problem, rows split over the ranks)
+class DistributedSinkhorn:
+    """``sinkhorn_algorithm`` (index/models/layers.py:85-108) for a batch whose rows are sharded over the ranks of
+    ``group``: the kernel all-reduces the column marginals itself through peer memory (NVLink P2P on symmetric
+    buffers, ``lcrec_sinkhorn_dense_dist``) - no collective is launched between iterations.  Reference semantics are
+    those of the single-device call on the concatenated batch.  Collective: every rank calls it."""
+
+    def __init__(self, n_codes: int, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.n_codes = int(n_codes)
+        self.device = torch.device(device)
+        nbytes = int(self.lib.lcrec_sinkhorn_dist_symmetric_bytes(self.n_codes))
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.world, self.rank = int(self.hdl.world_size), int(self.hdl.rank)
+        self.peers = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.epoch = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)          # every buffer is zeroed and mapped before the first kernel polls it
+
+    def center(self, d_local: torch.Tensor) -> torch.Tensor:
+        """center_distance_for_constraint (vq.py:51-61) with the max / min taken over the GLOBAL batch."""
+        mm = torch.stack([d_local.max(), -d_local.min()]) if d_local.numel() else torch.full((2,), -float("inf"), device=self.device)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=self.group)
+        mx, mn = mm[0], -mm[1]
+        mid = (mx + mn) / 2
+        amp = mx - mid + 1e-5
+        return (d_local - mid) / amp
+
+    def __call__(self, distances_local: torch.Tensor, epsilon: float, iters: int, n_rows_global: int = None):
+        import ctypes as C
+        from . import _lib
+        from .ops import _p, _stream, _ws
+        d = distances_local.detach().to(torch.float64).contiguous()
+        b, k = d.shape
+        assert k == self.n_codes and d.is_cuda
+        if n_rows_global is None:
+            t = torch.tensor([b], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, group=self.group)
+            n_rows_global = int(t.item())
+        q = torch.empty_like(d)
+        arg = torch.empty((b,), dtype=torch.int64, device=self.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ws = _ws(self.lib.lcrec_sinkhorn_workspace_bytes(max(b, 1), k), self.device)
+        epoch = self.epoch
+        self.epoch += int(iters) + 2
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lcrec_sinkhorn_dense_dist(_p(d), b, int(n_rows_global), k, float(epsilon), int(iters), _p(q), _p(arg),
+                                                          _p(flags), _p(self.peers), self.world, self.rank, C.c_uint64(epoch),
+                                                          _p(ws), ws.numel(), _stream(d)))
+        return q, arg, flags

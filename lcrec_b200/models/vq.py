@@ -27,6 +27,9 @@ class VectorQuantizer(nn.Module):
         self.sk_iters = sk_iters
         self.embedding = nn.Embedding(n_e, e_dim)
         self.initted = not kmeans_init
+        # data-parallel training: a lcrec_b200.distributed.DistributedSinkhorn makes the Sinkhorn step ONE problem over
+        # the global batch (rows sharded over the ranks, column marginals all-reduced inside the kernel); None = local
+        self.dist_sinkhorn = None
         if kmeans_init:
             self.embedding.weight.data.zero_()                       # filled by init_emb on the first batch
         else:
@@ -59,8 +62,14 @@ class VectorQuantizer(nn.Module):
         if not use_sk or self.sk_epsilon <= 0:
             return ops.rq_quantize(latent, [cb])["codes"][:, 0]
         d = ops.vq_distances(latent, cb)
-        dc = ops.center_distances(d)                                  # fp64, raises AssertionError like vq.py:59
-        _, idx, flags = ops.sinkhorn_dense(dc, self.sk_epsilon, self.sk_iters, want_argmax=True)
+        if self.dist_sinkhorn is not None:
+            dc = self.dist_sinkhorn.center(d)                          # max / min over the global batch
+            _, idx, flags = self.dist_sinkhorn(dc, self.sk_epsilon, self.sk_iters)
+            if int(flags.item()) & 8:
+                raise RuntimeError("distributed Sinkhorn: a peer rank did not arrive")
+        else:
+            dc = ops.center_distances(d)                              # fp64, raises AssertionError like vq.py:59
+            _, idx, flags = ops.sinkhorn_dense(dc, self.sk_epsilon, self.sk_iters, want_argmax=True)
         if int(flags.item()) & 1:
             print("Sinkhorn Algorithm returns nan/inf values.")        # vq.py:81-82
         return idx
