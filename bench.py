@@ -118,7 +118,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "25"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 
