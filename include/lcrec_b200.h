@@ -75,6 +75,16 @@ int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, const float* 
                          int n_out, int relu, float* y, int acc_chunk, int variant, void* ws,
                          int64_t ws_bytes, void* stream);
 
+/* Backward of one nn.Linear (+ fused ReLU) for the training step (trainer.py:114-118): with g = gy * (y_relu > 0)
+ * (y_relu = the layer's ReLU output, NULL when the forward did not fuse a ReLU): gb = column sums of g,
+ * gx = g W, gw = g^T x - both on the fp32-accurate split-operand tensor-core GEMMs (operands are transposed by a
+ * tiled copy so that the contraction dimension is contiguous).  Any of gx / gw / gb may be NULL.  k_in, n_out
+ * multiples of 4. */
+int64_t lcrec_linear_backward_workspace_bytes(int64_t n_rows, int k_in, int n_out);
+int lcrec_linear_backward(const float* x, const float* w, const float* y_relu, const float* gy, int64_t n_rows,
+                          int k_in, int n_out, float* gx, float* gw, float* gb, void* ws, int64_t ws_bytes,
+                          void* stream);
+
 /* ---- a3/a4/a7/a9: ResidualVectorQuantizer.forward, argmin branch ------------------------
  * (index/models/rq.py:39-56, vq.py:63-75,87-99).  One fused pass over all L levels:
  * d = (|r|^2 + |c|^2) - 2 r.c in fp32, lowest-index argmin, x_res = r + (q - r), r -= x_res.

@@ -759,3 +759,120 @@ extern "C" int lcrec_linear_forward(const float* x, int64_t n_rows, int k_in, co
   p.a_hi = a_hi; p.a_lo = a_lo; p.lda = ldk; p.w_hi = w_hi; p.w_lo = w_lo; p.ldw = ldk;
   return launch_linear(p, st);
 }
+
+// ====================================================================== backward of one Linear(+ReLU)
+// Training path (trainer.py:114-118: loss.backward()): for y = relu?(x W^T + b)
+//   g  = gy * (y > 0)            (ReLU mask, only when the forward fused the ReLU)
+//   gb = sum_rows g              gx = g W              gw = g^T x
+// Both GEMMs run on the same fp32-accurate split-operand tensor-core kernels as the forward (the contraction
+// dimension has to be the fastest one of both operands, so W, g and x are transposed by a tiled copy first).
+namespace lcrec {
+
+// out (cols x ldo) = in (rows x cols)^T, ldo >= rows
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols,
+                                                        float* __restrict__ out, int64_t ldo) {
+  __shared__ float tile[32][33];
+  const int64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  for (int64_t t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const int64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8)
+      if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = in[(r0 + j) * cols + c0 + tx];
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8)
+      if (c0 + j < cols && r0 + tx < rows) out[(c0 + j) * ldo + r0 + tx] = tile[tx][j];
+    __syncthreads();
+  }
+}
+
+// g = gy * (y > 0) (y null: g = gy) and gb[c] = sum over rows of g[:, c]; one CTA per 32 columns, fixed summation order
+__global__ void __launch_bounds__(256) relu_mask_bias_grad_kernel(const float* __restrict__ gy, const float* __restrict__ y,
+                                                                  int64_t rows, int cols, float* __restrict__ g,
+                                                                  float* __restrict__ gb) {
+  __shared__ float red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c0 = blockIdx.x * 32; c0 < cols; c0 += gridDim.x * 32) {
+    const int c = c0 + tx;
+    float s = 0.f;
+    if (c < cols)
+      for (int64_t r = ty; r < rows; r += 8) {
+        float v = gy[r * cols + c];
+        if (y != nullptr && !(y[r * cols + c] > 0.f)) v = 0.f;
+        if (g != nullptr) g[r * cols + c] = v;
+        s += v;
+      }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols && gb != nullptr) {
+      float t = 0.f;
+      for (int j = 0; j < 8; ++j) t += red[j][tx];
+      gb[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+static int launch_transpose(const float* in, int64_t rows, int64_t cols, float* out, int64_t ldo, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return LCREC_OK;
+  const int64_t tiles = ceil_div(rows, 32) * ceil_div(cols, 32);
+  transpose_kernel<<<(unsigned)std::min<int64_t>(tiles, (int64_t)num_sms() * 16), 256, 0, st>>>(in, rows, cols, out, ldo);
+  LC_LAUNCH_CHECK("transpose_kernel");
+  return LCREC_OK;
+}
+
+static inline int64_t pad8(int64_t v) { return round_up(std::max<int64_t>(v, 1), 8); }
+
+}  // namespace lcrec
+
+extern "C" int64_t lcrec_linear_backward_workspace_bytes(int64_t n_rows, int k_in, int n_out) {
+  const int64_t nr = pad8(n_rows);
+  // g, g^T (padded batch), x^T (padded batch), W^T + the workspaces of the two GEMM calls
+  return arena_need(sizeof(float) * n_rows * n_out) + arena_need(sizeof(float) * (int64_t)n_out * nr) +
+         arena_need(sizeof(float) * (int64_t)k_in * nr) + arena_need(sizeof(float) * (int64_t)k_in * n_out) +
+         std::max(lcrec_linear_workspace_bytes(n_rows, n_out, k_in), lcrec_linear_workspace_bytes(n_out, (int)nr, k_in)) + 1024;
+}
+
+extern "C" int lcrec_linear_backward(const float* x, const float* w, const float* y_relu, const float* gy, int64_t n_rows,
+                                     int k_in, int n_out, float* gx, float* gw, float* gb, void* ws, int64_t ws_bytes,
+                                     void* stream) {
+  LC_ARG(n_rows >= 0 && k_in > 0 && n_out > 0 && (k_in & 3) == 0 && (n_out & 3) == 0);
+  LC_TRY(lcrec_device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rows == 0) {
+    if (gw) LC_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)n_out * k_in, st));
+    if (gb) LC_CUDA(cudaMemsetAsync(gb, 0, sizeof(float) * n_out, st));
+    return LCREC_OK;
+  }
+  LC_ARG(gy != nullptr && (gx == nullptr || w != nullptr) && (gw == nullptr || x != nullptr));
+  const int64_t nr = pad8(n_rows);
+  Arena ar(ws, ws_bytes);
+  float* g = ar.take<float>(n_rows * n_out);
+  float* gt = ar.take<float>((int64_t)n_out * nr);
+  float* xt = ar.take<float>((int64_t)k_in * nr);
+  float* wt = ar.take<float>((int64_t)k_in * n_out);
+  const int64_t sub_bytes = std::max(lcrec_linear_workspace_bytes(n_rows, n_out, k_in), lcrec_linear_workspace_bytes(n_out, (int)nr, k_in));
+  char* sub = ar.take<char>(sub_bytes);
+  if (!ar.ok()) { set_error("linear_backward: workspace too small (%lld given, %lld needed)", (long long)ws_bytes, (long long)lcrec_linear_backward_workspace_bytes(n_rows, k_in, n_out)); return LCREC_ERR_NOMEM; }
+  const float* gsrc = gy;
+  if (y_relu != nullptr || gb != nullptr) {
+    relu_mask_bias_grad_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n_out, 32), (int64_t)num_sms() * 4), 256, 0, st>>>(
+        gy, y_relu, n_rows, n_out, y_relu ? g : nullptr, gb);
+    LC_LAUNCH_CHECK("relu_mask_bias_grad_kernel");
+    if (y_relu) gsrc = g;
+  }
+  auto variant_for = [](int k, int n) { return linear_pair_supported(k, n, kPairGroup) ? 6 : 2; };
+  if (gx != nullptr) {      // gx (n x K) = g (n x N) . W (N x K): "weights" = W^T (K x N), contraction over N
+    LC_TRY(launch_transpose(w, n_out, k_in, wt, n_out, st));
+    LC_TRY(lcrec_linear_forward(gsrc, n_rows, n_out, wt, nullptr, k_in, 0, gx, 64, variant_for(n_out, k_in), sub, sub_bytes, stream));
+  }
+  if (gw != nullptr) {      // gw (N x K) = g^T (N x n) . x (n x K): "weights" = x^T (K x n), contraction over the batch
+    if (nr != n_rows) {     // zero the padded batch columns (the split kernels read whole rows)
+      LC_CUDA(cudaMemsetAsync(gt, 0, sizeof(float) * (size_t)n_out * nr, st));
+      LC_CUDA(cudaMemsetAsync(xt, 0, sizeof(float) * (size_t)k_in * nr, st));
+    }
+    LC_TRY(launch_transpose(gsrc, n_rows, n_out, gt, nr, st));
+    LC_TRY(launch_transpose(x, n_rows, k_in, xt, nr, st));
+    LC_TRY(lcrec_linear_forward(gt, n_out, (int)nr, xt, nullptr, k_in, 0, gw, 64, variant_for((int)nr, k_in), sub, sub_bytes, stream));
+  }
+  return LCREC_OK;
+}

@@ -38,8 +38,8 @@ def activation_layer(activation_name="relu", emb_dim=None):
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = relu?(x W^T + b): forward on the tcgen05 kernel; backward GEMMs are plain library
-    matmuls (fp32, TF32 off) - see DESIGN.md "training path"."""
+    """y = relu?(x W^T + b): forward and backward (ReLU mask, bias gradient, gx = g W, gw = g^T x) on the
+    fp32-accurate split-operand tcgen05 kernels (lcrec_linear_forward / lcrec_linear_backward)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, fuse_relu: bool):
@@ -52,17 +52,9 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        if ctx.fuse_relu:
-            gy = gy * (y > 0).to(gy.dtype)
-        gy2 = gy.reshape(-1, gy.shape[-1])
-        x2 = x.reshape(-1, x.shape[-1])
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            gx = (gy2 @ weight).reshape(x.shape)
-        if ctx.needs_input_grad[1]:
-            gw = gy2.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(0)
+        gx, gw, gb = ops.linear_backward(x, weight, y if ctx.fuse_relu else None, gy,
+                                         need_gx=ctx.needs_input_grad[0], need_gw=ctx.needs_input_grad[1],
+                                         need_gb=ctx.has_bias and ctx.needs_input_grad[2])
         return gx, gw, gb, None
 
 

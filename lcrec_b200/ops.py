@@ -161,6 +161,26 @@ def linear_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], 
     return y.reshape(*x.shape[:-1], m)
 
 
+def linear_backward(x: torch.Tensor, w: torch.Tensor, y_relu: Optional[torch.Tensor], gy: torch.Tensor,
+                    need_gx: bool = True, need_gw: bool = True, need_gb: bool = True):
+    """Gradients of relu?(x @ w.T + b) (autograd of nn.Linear + ReLU, trainer.py:114-118) on the split-operand
+    tensor-core kernels: returns (gx, gw, gb), None for the ones not requested."""
+    _need_cuda(x, w, gy)
+    lib = _lib.load()
+    m, k = w.shape
+    x2, w2, g2 = _f32c(x.reshape(-1, k)), _f32c(w), _f32c(gy.reshape(-1, m))
+    y2 = None if y_relu is None else _f32c(y_relu.reshape(-1, m))
+    n = x2.shape[0]
+    gx = torch.empty((n, k), dtype=torch.float32, device=x2.device) if need_gx else None
+    gw = torch.empty((m, k), dtype=torch.float32, device=x2.device) if need_gw else None
+    gb = torch.empty((m,), dtype=torch.float32, device=x2.device) if need_gb else None
+    ws = _ws(lib.lcrec_linear_backward_workspace_bytes(n, k, m), x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.lcrec_linear_backward(_p(x2), _p(w2), _p(y2), _p(g2), n, k, m, _p(gx), _p(gw), _p(gb), _p(ws),
+                                             ws.numel(), _stream(x2)))
+    return (None if gx is None else gx.reshape(x.shape)), gw, gb
+
+
 # --------------------------------------------------------------------------- RQ
 def rq_set_tc_mode(mode: int) -> None:
     """0 = SIMT kernels only, 1 = tensor-core distance GEMM for large codebooks (default), 2 = whenever possible."""

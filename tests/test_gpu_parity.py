@@ -64,6 +64,29 @@ def test_linear_matches_fp64(n, k, m, relu):
         assert (y.double() - ref).abs().mean().item() <= max(3.0 * err32, 2e-7 * scale)
 
 
+@pytest.mark.parametrize("n,k,m", [(1024, 4096, 2048), (424, 512, 256), (37, 96, 64), (16, 32, 32), (1000, 256, 512), (1024, 32, 4096)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_linear_backward_matches_fp64(n, k, m, relu):
+    """gx = g W, gw = g^T x, gb = sum g with g = gy * (y > 0): the training backward on the split-operand tensor-core
+    GEMMs (pair kernel where the shape allows, batch sizes that are not multiples of 8 included) vs fp64."""
+    g = torch.Generator(device=DEV).manual_seed(n + 3 * k + m)
+    x = torch.randn(n, k, device=DEV, generator=g)
+    w = torch.randn(m, k, device=DEV, generator=g) * (2.0 / (k + m)) ** 0.5
+    b = torch.randn(m, device=DEV, generator=g) * 0.01
+    gy = torch.randn(n, m, device=DEV, generator=g)
+    y = ops.linear_forward(x, w, b, relu)
+    gx, gw, gb = ops.linear_backward(x, w, y if relu else None, gy)
+    gd = gy.double() * (y > 0).double() if relu else gy.double()
+    for got, ref, a_abs, b_abs in ((gx, gd @ w.double(), gd.abs(), w.double().abs()),
+                                   (gw, gd.t() @ x.double(), gd.abs().t(), x.double().abs())):
+        scale = (a_abs @ b_abs).mean().item() + 1e-30
+        assert (got.double() - ref).abs().max().item() / scale < 2e-6
+    ref_b = gd.sum(0)
+    assert (gb.double() - ref_b).abs().max().item() <= 1e-5 * gd.abs().sum(0).max().item() + 1e-30
+    only_w = ops.linear_backward(x, w, None, gy, need_gx=False, need_gb=False)
+    assert only_w[0] is None and only_w[2] is None and only_w[1].shape == (m, k)
+
+
 def test_linear_zero_rows_and_errors():
     w = torch.randn(8, 8, device=DEV)
     assert ops.linear_forward(torch.zeros(0, 8, device=DEV), w, None, True).shape == (0, 8)
