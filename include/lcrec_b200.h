@@ -60,6 +60,9 @@ int lcrec_mlp_set_acc_chunk(lcrec_mlp_t* mlp, int k_elems);
  * 4 = no TMA loads after the first ring fill, 8 = no MMAs (4 and 8: timing experiments, results are garbage),
  * 16 = never use the CTA-pair kernel, 32 = CTA-pair kernel with 6 x 32 KB stages instead of 3 x 64 KB. */
 int lcrec_mlp_set_variant(lcrec_mlp_t* mlp, int variant);
+/* persistent grid of the CTA-pair GEMM limited to `cap` CTA pairs (0 = all 74): leaves SMs to kernels that run
+ * concurrently on other streams (the pair GEMM is power-bound, memory-bound stages are not) */
+int lcrec_pair_set_cluster_cap(int cap);
 /* measurement only: device buffer of 6 x 512 x 4 int64 that receives clock64 stamps of the pipeline roles of
  * one CTA of the layer-0 pair kernel (producer / MMA k-blocks / MMA chunks / fold), or NULL to switch off. */
 int lcrec_mlp_set_trace(lcrec_mlp_t* mlp, void* trace);
@@ -193,6 +196,15 @@ int lcrec_collisions_in_segments(const int64_t* codes, int64_t n, int n_levels, 
                                  const int64_t* seg_offsets, const int64_t* seg_members, const int64_t* n_segs_dev,
                                  int64_t max_segments, int64_t* offsets, int64_t* members, int64_t* counts,
                                  void* ws, int64_t ws_bytes, void* stream);
+/* same with an explicit active list (device int32 arrays): only the segments named by active_in / n_active_in are
+ * examined (NULL = all), the segments that still contain a collision are appended to active_out / n_active_out
+ * (NULL = not wanted; *n_active_out must be 0 on entry) - a segment without a collision cannot acquire one later. */
+int lcrec_collisions_in_segments_active(const int64_t* codes, int64_t n, int n_levels, int level,
+                                        const int64_t* seg_offsets, const int64_t* seg_members,
+                                        const int64_t* n_segs_dev, int64_t max_segments, const int32_t* active_in,
+                                        const int32_t* n_active_in, int32_t* active_out, int32_t* n_active_out,
+                                        int64_t* offsets, int64_t* members, int64_t* counts, void* ws, int64_t ws_bytes,
+                                        void* stream);
 /* sorted (key, item) pairs only; keys_out/items_out (n) */
 int lcrec_sort_codes(const int64_t* codes, int64_t n, int n_levels, const int32_t* n_codes,
                      uint64_t* keys_out, uint32_t* items_out, void* ws, int64_t ws_bytes, void* stream);

@@ -31,6 +31,7 @@ SIGNATURES = {
     "lcrec_mlp_set_variant": (C.c_int, [vp, C.c_int]),
     "lcrec_mlp_set_engine": (C.c_int, [vp, C.c_int]),
     "lcrec_mlp_set_trace": (C.c_int, [vp, vp]),
+    "lcrec_pair_set_cluster_cap": (C.c_int, [C.c_int]),
     "lcrec_mlp_in_dim": (C.c_int, [vp]),
     "lcrec_mlp_out_dim": (C.c_int, [vp]),
     "lcrec_linear_workspace_bytes": (i64, [i64, C.c_int, C.c_int]),
@@ -60,6 +61,8 @@ SIGNATURES = {
     "lcrec_prefix_segments": (C.c_int, [vp, i64, C.c_int, C.POINTER(i32), vp, vp, vp, vp, i64, vp]),
     "lcrec_segment_collisions_workspace_bytes": (i64, [i64]),
     "lcrec_collisions_in_segments": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
+    "lcrec_collisions_in_segments_active": (C.c_int, [vp, i64, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                      i64, vp]),
     "lcrec_profile_enable": (C.c_int, [C.c_int]),
     "lcrec_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(i64)]),
     "lcrec_indexer_create": (C.c_int, [vp, C.c_int, C.c_int, pp, C.POINTER(i32), f64, C.c_int, i64, i64, pp]),

@@ -134,6 +134,7 @@ struct lcrec_indexer {
   void* sk_ws = nullptr; int64_t sk_ws_bytes = 0;
   int64_t* seg_offsets = nullptr; int64_t* seg_members = nullptr; int64_t* seg_counts = nullptr;   // prefix segments
   void* seg_ws = nullptr; int64_t seg_ws_bytes = 0;
+  int32_t* seg_active[2] = {nullptr, nullptr}; int32_t* seg_active_count = nullptr;   // ping-pong lists + 2 counters
   float* stage[2] = {nullptr, nullptr};
   int64_t* counts_host = nullptr;   // pinned: 4 counts + flags
   cudaStream_t copy_stream = nullptr;
@@ -182,6 +183,9 @@ extern "C" int lcrec_indexer_create(lcrec_mlp_t* encoder, int e_dim, int n_level
   IX_ALLOC(ix->seg_counts, sizeof(int64_t) * 8);
   ix->seg_ws_bytes = lcrec_segment_collisions_workspace_bytes(max_items / 2 + 1);
   IX_ALLOC(ix->seg_ws, ix->seg_ws_bytes);
+  IX_ALLOC(ix->seg_active[0], sizeof(int32_t) * (max_items / 2 + 2));
+  IX_ALLOC(ix->seg_active[1], sizeof(int32_t) * (max_items / 2 + 2));
+  IX_ALLOC(ix->seg_active_count, sizeof(int32_t) * 2);
   if (cudaMallocHost((void**)&ix->counts_host, sizeof(int64_t) * 8) != cudaSuccess) {
     set_error("indexer: cudaMallocHost failed"); lcrec_indexer_destroy(ix); return LCREC_ERR_NOMEM;
   }
@@ -194,6 +198,7 @@ extern "C" int lcrec_indexer_destroy(lcrec_indexer_t* ix) {
   cudaFree(ix->codes); cudaFree(ix->resid); cudaFree(ix->z); cudaFree(ix->mlp_ws); cudaFree(ix->offsets);
   cudaFree(ix->members); cudaFree(ix->counts); cudaFree(ix->col_ws); cudaFree(ix->sk_ws);
   cudaFree(ix->seg_offsets); cudaFree(ix->seg_members); cudaFree(ix->seg_counts); cudaFree(ix->seg_ws);
+  cudaFree(ix->seg_active[0]); cudaFree(ix->seg_active[1]); cudaFree(ix->seg_active_count);
   cudaFree(ix->stage[0]); cudaFree(ix->stage[1]);
   if (ix->counts_host) cudaFreeHost(ix->counts_host);
   for (int i = 0; i < 2; ++i) { if (ix->ev_copied[i]) cudaEventDestroy(ix->ev_copied[i]); if (ix->ev_consumed[i]) cudaEventDestroy(ix->ev_consumed[i]); }
@@ -230,13 +235,20 @@ extern "C" int lcrec_indexer_set_segments(int on) { g_use_segments = on ? 1 : 0;
 
 // One collision check of codes (n x L) into ix->offsets / members / counts, counts copied to the pinned host block
 // (8 int64: n_unique, n_groups, rows, max_mult, flag words, segment fallback).  Synchronises the stream.
-static int collide_and_fetch(lcrec_indexer_t* ix, const int64_t* codes, int64_t n, bool in_segments, cudaStream_t st) {
+// seg_round: -1 = global sort; k >= 0 = k-th check inside the prefix segments (0 examines all segments, later ones
+// only those that collided in the previous check)
+static int collide_and_fetch(lcrec_indexer_t* ix, const int64_t* codes, int64_t n, int seg_round, cudaStream_t st) {
   {
     ProfScope prof(21, st);
-    if (in_segments)
-      LC_TRY(lcrec_collisions_in_segments(codes, n, ix->L, ix->L - 1, ix->seg_offsets, ix->seg_members, ix->seg_counts + 1,
-                                          n / 2 + 1, ix->offsets, ix->members, ix->counts, ix->seg_ws, ix->seg_ws_bytes, st));
-    else
+    if (seg_round >= 0) {
+      const int in = (seg_round + 1) & 1, out = seg_round & 1;
+      LC_CUDA(cudaMemsetAsync(ix->seg_active_count + out, 0, sizeof(int32_t), st));
+      LC_TRY(lcrec_collisions_in_segments_active(codes, n, ix->L, ix->L - 1, ix->seg_offsets, ix->seg_members, ix->seg_counts + 1,
+                                                 n / 2 + 1, seg_round > 0 ? ix->seg_active[in] : nullptr,
+                                                 seg_round > 0 ? ix->seg_active_count + in : nullptr, ix->seg_active[out],
+                                                 ix->seg_active_count + out, ix->offsets, ix->members, ix->counts, ix->seg_ws,
+                                                 ix->seg_ws_bytes, st));
+    } else
       LC_TRY(lcrec_collisions(codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
                               ix->col_ws_bytes, st));
   }
@@ -256,15 +268,16 @@ static int rounds_impl(lcrec_indexer_t* ix, int64_t* codes, const float* resid, 
                        cudaStream_t st) {
   int64_t rounds = 0, g1 = 0, r1 = 0, tot_rows = 0;
   bool use_seg = g_use_segments && ix->L >= 2, have_seg = false;
+  int seg_round = 0;
   LC_CUDA(cudaMemsetAsync(ix->counts, 0, sizeof(int64_t) * 8, st));     // incl. the flag words (accumulated by atomicOr)
   const int64_t* c = ix->counts_host;
   while (true) {
     const bool resolve = rounds < max_rounds;
-    LC_TRY(collide_and_fetch(ix, codes, n, have_seg, st));
+    LC_TRY(collide_and_fetch(ix, codes, n, have_seg ? seg_round++ : -1, st));
     if (have_seg && c[5] != 0) {            // a segment too large for the on-chip sort: back to the global sort for good
       have_seg = use_seg = false;
       LC_CUDA(cudaMemsetAsync(ix->counts + 5, 0, sizeof(int64_t), st));
-      LC_TRY(collide_and_fetch(ix, codes, n, false, st));
+      LC_TRY(collide_and_fetch(ix, codes, n, -1, st));
     }
     LC_TRY(check_flags((int32_t)(c[4] & 0xffffffff)));
     const int64_t groups = c[1], rows = c[2];
@@ -315,7 +328,7 @@ extern "C" int lcrec_indexer_round(lcrec_indexer_t* ix, int64_t n, int64_t* coun
   LC_ARG(ix && n >= 0 && n <= ix->max_items);
   cudaStream_t st = (cudaStream_t)stream;
   LC_CUDA(cudaMemsetAsync(ix->counts, 0, sizeof(int64_t) * 8, st));
-  LC_TRY(collide_and_fetch(ix, ix->codes, n, false, st));
+  LC_TRY(collide_and_fetch(ix, ix->codes, n, -1, st));
   const int64_t groups = ix->counts_host[1], rows = ix->counts_host[2];
   if (groups > 0) {
     ProfScope prof(22, st);

@@ -237,17 +237,25 @@ __global__ void __launch_bounds__(256) segment_collisions_kernel(const int64_t* 
                                                                  const int64_t* __restrict__ seg_members,
                                                                  const int64_t* __restrict__ n_segs_dev,
                                                                  int64_t* __restrict__ offsets, int64_t* __restrict__ members,
-                                                                 unsigned long long* __restrict__ ctl, int32_t* __restrict__ big_list) {
+                                                                 unsigned long long* __restrict__ ctl, int32_t* __restrict__ big_list,
+                                                                 const int32_t* __restrict__ active_in, const int* __restrict__ n_active_in,
+                                                                 int32_t* __restrict__ active_out, int* __restrict__ n_active_out) {
   const int lane = threadIdx.x & 31;
-  const int64_t n_segs = *n_segs_dev;
+  // a segment without a collision this round cannot have one later (nothing in it changes): from the second check
+  // on only the segments that collided last time (active_in) are examined, and those that still collide are passed on
+  const int64_t n_segs = active_in ? (int64_t)*n_active_in : *n_segs_dev;
   long long local_max = 0;
-  for (int64_t sg = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; sg < n_segs; sg += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < n_segs; w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t sg = active_in ? (int64_t)active_in[w] : w;
     const int64_t beg = seg_offsets[sg];
     const int m = (int)min((int64_t)(kSegMax + 1), seg_offsets[sg + 1] - beg);
     if (m > 32) {
       if (lane == 0) {
         if (m > kSegMax) atomicExch(ctl + 3, 1ull);
-        else big_list[atomicAdd(ctl + 2, 1ull)] = (int32_t)sg;
+        else {
+          big_list[atomicAdd(ctl + 2, 1ull)] = (int32_t)sg;
+          if (active_out) active_out[atomicAdd(n_active_out, 1)] = (int32_t)sg;      // big segments stay on the list
+        }
       }
       continue;
     }
@@ -273,7 +281,10 @@ __global__ void __launch_bounds__(256) segment_collisions_kernel(const int64_t* 
     const unsigned heads = __ballot_sync(0xffffffffu, !eq_prev && eq_next);
     if (in_run == 0) continue;
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(ctl, ((unsigned long long)__popc(heads) << 32) | (unsigned long long)__popc(in_run));
+    if (lane == 0) {
+      base = atomicAdd(ctl, ((unsigned long long)__popc(heads) << 32) | (unsigned long long)__popc(in_run));
+      if (active_out) active_out[atomicAdd(n_active_out, 1)] = (int32_t)sg;
+    }
     base = __shfl_sync(0xffffffffu, base, 0);
     const int64_t rb = (int64_t)(base & 0xffffffffull), gb = (int64_t)(base >> 32);
     const unsigned below = (1u << lane) - 1u;
@@ -505,11 +516,32 @@ extern "C" int64_t lcrec_segment_collisions_workspace_bytes(int64_t max_segments
 // Collision groups of the current codes[:, level] inside the prefix segments (see above).  counts (device, 8 int64):
 // [n_unique, n_groups, rows, max_multiplicity, -, fallback]; fallback = 1 means a segment was too large for the
 // on-chip sort and the result is incomplete: call lcrec_collisions instead.
+extern "C" int lcrec_collisions_in_segments_active(const int64_t* codes, int64_t n, int n_levels, int level,
+                                                   const int64_t* seg_offsets, const int64_t* seg_members,
+                                                   const int64_t* n_segs_dev, int64_t max_segments, const int32_t* active_in,
+                                                   const int32_t* n_active_in, int32_t* active_out, int32_t* n_active_out,
+                                                   int64_t* offsets, int64_t* members, int64_t* counts, void* ws,
+                                                   int64_t ws_bytes, void* stream);
+
 extern "C" int lcrec_collisions_in_segments(const int64_t* codes, int64_t n, int n_levels, int level, const int64_t* seg_offsets,
                                             const int64_t* seg_members, const int64_t* n_segs_dev, int64_t max_segments,
                                             int64_t* offsets, int64_t* members, int64_t* counts, void* ws, int64_t ws_bytes,
                                             void* stream) {
+  return lcrec_collisions_in_segments_active(codes, n, n_levels, level, seg_offsets, seg_members, n_segs_dev, max_segments,
+                                             nullptr, nullptr, nullptr, nullptr, offsets, members, counts, ws, ws_bytes, stream);
+}
+
+// Same with an explicit active list: active_in / n_active_in (device; NULL = examine every segment) name the segments
+// to examine, active_out / n_active_out (device; NULL = not wanted; *n_active_out must be 0 on entry) receive the
+// segments that still contain a collision - the input of the next round.
+extern "C" int lcrec_collisions_in_segments_active(const int64_t* codes, int64_t n, int n_levels, int level,
+                                                   const int64_t* seg_offsets, const int64_t* seg_members,
+                                                   const int64_t* n_segs_dev, int64_t max_segments, const int32_t* active_in,
+                                                   const int32_t* n_active_in, int32_t* active_out, int32_t* n_active_out,
+                                                   int64_t* offsets, int64_t* members, int64_t* counts, void* ws,
+                                                   int64_t ws_bytes, void* stream) {
   LC_ARG(n >= 0 && n_levels >= 1 && level >= 0 && level < n_levels && max_segments >= 0 && counts);
+  LC_ARG((active_in == nullptr) == (n_active_in == nullptr) && (active_out == nullptr) == (n_active_out == nullptr));
   LC_TRY(lcrec_device_check());
   cudaStream_t st = (cudaStream_t)stream;
   LC_ARG(codes && seg_offsets && seg_members && n_segs_dev && offsets && members);
@@ -521,7 +553,8 @@ extern "C" int lcrec_collisions_in_segments(const int64_t* codes, int64_t n, int
   if (max_segments > 0) {
     const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_segments, 8), (int64_t)num_sms() * 8));
     segment_collisions_kernel<<<(unsigned)blocks, 256, 0, st>>>(codes, n_levels, level, seg_offsets, seg_members, n_segs_dev,
-                                                                 offsets, members, ctl, big_list);
+                                                                 offsets, members, ctl, big_list, active_in, n_active_in,
+                                                                 active_out, n_active_out);
     LC_LAUNCH_CHECK("segment_collisions_kernel");
     segment_collisions_big_kernel<<<(unsigned)std::min<int64_t>(max_segments, num_sms()), 256, 0, st>>>(
         codes, n_levels, level, seg_offsets, seg_members, offsets, members, ctl, big_list);

@@ -39,6 +39,7 @@ int launch_linear_pair(const PairProblem& p, cudaStream_t st);
 bool linear_pair_supported(int k, int n_out, int group);
 int launch_argmin_pair(const PairProblem& p, cudaStream_t st);
 bool argmin_pair_supported(int k, int n_out);
+void set_pair_cluster_cap(int cap);   // 0 = all CTA pairs the device holds
 constexpr int kPairGroup = 256;
 
 // x (rows, k) fp32 -> group-scaled fp16 hi/lo (one pass; scale groups of 256 elements)

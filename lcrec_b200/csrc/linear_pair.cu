@@ -445,6 +445,8 @@ __global__ void __launch_bounds__(256) split_groups_kernel(const float* __restri
   }
 }
 
+int g_pair_cluster_cap = 0;     // > 0: persistent grid limited to this many CTA pairs (leaves SMs to concurrent kernels)
+
 template <int BK, int STAGES, bool ARGMIN>
 int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
   using C = PairCfg<BK, STAGES>;
@@ -478,13 +480,17 @@ int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
   a.o_hi = p.o_hi; a.o_lo = p.o_lo; a.ldo = p.ldo; a.o_inv_scale = p.o_inv_scale; a.ld_oscale = p.ld_oscale;
   a.debug = p.debug; a.trace = (long long*)p.trace;
   a.xx = p.xx; a.cc = p.cc; a.codes = p.codes; a.codes_stride = p.codes_stride;
-  const int64_t clusters = std::min<int64_t>(ARGMIN ? a.n_tiles / a.tiles_n : a.n_tiles, max_clusters);
+  int cap = max_clusters;
+  if (g_pair_cluster_cap > 0) cap = std::min(cap, g_pair_cluster_cap);
+  const int64_t clusters = std::min<int64_t>(ARGMIN ? a.n_tiles / a.tiles_n : a.n_tiles, cap);
   kern<<<(unsigned)(2 * clusters), kPairThreads, C::SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, a);
   LC_LAUNCH_CHECK("linear_pair_kernel");
   return LCREC_OK;
 }
 
 }  // namespace
+
+void set_pair_cluster_cap(int cap) { g_pair_cluster_cap = cap; }
 
 bool linear_pair_supported(int k, int n_out, int group) {
   return group == kGroup && n_out >= kTileN && n_out % kTileN == 0 && k >= 64 && k % 8 == 0;

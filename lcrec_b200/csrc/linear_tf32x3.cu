@@ -547,6 +547,12 @@ extern "C" int lcrec_mlp_set_variant(lcrec_mlp_t* m, int variant) {
   return LCREC_OK;
 }
 
+extern "C" int lcrec_pair_set_cluster_cap(int cap) {
+  LC_ARG(cap >= 0);
+  set_pair_cluster_cap(cap);
+  return LCREC_OK;
+}
+
 extern "C" int lcrec_mlp_set_trace(lcrec_mlp_t* m, void* trace) {
   LC_ARG(m != nullptr);
   m->trace = trace;
