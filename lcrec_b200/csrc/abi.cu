@@ -290,7 +290,7 @@ static int rounds_impl(lcrec_indexer_t* ix, int64_t* codes, const float* resid, 
       have_seg = true;
     }
     {
-      ProfScope prof(22, st);
+      ProfScope prof(rounds == 0 ? 22 : 23, st);      // 22 = first round, 23 = later rounds
       LC_TRY(lcrec_sinkhorn_groups_ex(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members,
                                       ix->counts + 1, groups, rows, c[3], ix->eps, ix->iters, codes, ix->L, ix->L - 1, 1, 0,
                                       ix->flags, ix->sk_ws, ix->sk_ws_bytes, st));

@@ -54,7 +54,8 @@ inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
 int num_sms();
 
 // Optional per-stage device timing (CUDA events on the launching stream), used by bench.py for the
-// live roofline figure.  Tags: 0 = split, 1..16 = MLP layer l, 20 = rq, 21 = collide, 22 = sinkhorn.
+// live roofline figure.  Tags: 0 = split, 1..16 = MLP layer l, 17 = tail splits, 20 = rq, 21 = collide, 22 = sinkhorn of the
+// first round, 23 = sinkhorn of the later rounds, 24 = warp-class kernels / 26 = literal re-run inside a sinkhorn call.
 constexpr int kProfTags = 32;
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);

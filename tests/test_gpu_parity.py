@@ -491,6 +491,57 @@ def test_segment_rounds_equal_global_sort_rounds():
     assert torch.equal(codes.cpu(), c1.cpu()) and s2["n_unique"] == s1["n_unique"]
 
 
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_generation_equals_single_gpu_bitwise():
+    """2 ranks (NCCL all-to-all bucket exchange + native rounds per owner) == the single-GPU table, bit for bit."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29578", os.path.join(root, "scripts", "check_sharded_equals_single.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["ok"] and out["identical"]
+
+
+def test_full_size_generation_properties():
+    """BASELINE configs[2] size (1 M items x 4096): size-independent properties of the whole path - determinism, the
+    statistics describe the table, items whose PASS-0 code was unique are untouched, a second resolve of the final
+    table only touches what still collides, and the prefix (first L-1 levels) never changes."""
+    import bench
+    ws, bs, cbs, head = bench.make_model()
+    m = RQVAE(in_dim=4096, num_emb_list=bench.N_CODES, e_dim=32, layers=bench.DIMS[1:-1], sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50)
+    sd = m.state_dict()
+    lin = sorted([k for k in sd if k.startswith("encoder.mlp_layers.") and k.endswith(".weight")], key=lambda s: int(s.split(".")[2]))
+    for k, w, b in zip(lin, ws, bs):
+        sd[k] = torch.from_numpy(w); sd[k.replace(".weight", ".bias")] = torch.from_numpy(b)
+    for l, cb in enumerate(cbs):
+        sd[f"rq.vq_layers.{l}.embedding.weight"] = torch.from_numpy(cb)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    n = 1_000_000
+    x = bench.make_items_device(n, head, DEV, 0)
+    ix = G.build_indexer(m, n)
+    c1, s1 = ix.run_device(x, 20)
+    c2, s2 = ix.run_device(x, 20)
+    assert torch.equal(c1, c2) and s1 == s2                                   # deterministic
+    ix.pass0(x)
+    pass0 = ix.codes_view(n).clone()
+    assert torch.equal(pass0[:, :3], c1[:, :3])                               # the rounds rewrite the last level only
+    key = lambda c: (c[:, 0] << 24) | (c[:, 1] << 16) | (c[:, 2] << 8) | c[:, 3]
+    k0, k1 = key(pass0), key(c1)
+    assert int(torch.unique(k1).numel()) == s1["n_unique"]                    # the statistics describe the table
+    u, inv, cnt = torch.unique(k0, return_inverse=True, return_counts=True)
+    lonely = cnt[inv] == 1
+    assert s1["rows_round1"] == int((~lonely).sum()) and s1["groups_round1"] == int((cnt > 1).sum())
+    prefix_cnt = torch.unique(k0 >> 8, return_inverse=True, return_counts=True)
+    alone_in_prefix = prefix_cnt[2][prefix_cnt[1]] == 1
+    assert torch.equal(pass0[alone_in_prefix], c1[alone_in_prefix])           # nobody to collide with: never touched
+    assert (c1[:, 3] >= 0).all() and (c1[:, 3] < 256).all()
+    r = ops.collisions(c1, bench.N_CODES)
+    assert r["n_unique"] == s1["n_unique"] and r["n_rows"] == n - s1["n_unique"] + r["n_groups"]
+
+
 def test_generate_indices_empty_and_unique_inputs(golden):
     g, m, p = load_small(golden, "small_model")
     codes, stats = G.generate_codes(m, torch.zeros(0, 96, device=DEV))
