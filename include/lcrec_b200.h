@@ -38,7 +38,8 @@ int lcrec_device_check(void);
 /* ---- a2: MLPLayers.forward (index/models/layers.py:18-43) ------------------------------
  * y = relu(x W^T + b) per layer, last layer without ReLU unless relu_last.  Eval-mode
  * BatchNorm1d is folded into (W, b) by the caller.  fp32-accurate: every product is
- * evaluated as 3 TF32 tcgen05 MMAs (hi*hi + lo*hi + hi*lo) with fp32 accumulation.
+ * evaluated as 3 tcgen05 MMAs (hi*hi + lo*hi + hi*lo) on a two-term operand split (fp16 pairs
+ * with power-of-two scales by default, tf32 pairs with engine 0) with chunked fp32 accumulation.
  * `weights[i]` is (dims[i+1], dims[i]) row-major like nn.Linear.weight.  The handle owns
  * split copies of the weights; call lcrec_mlp_update() after the caller changes them.
  */
@@ -240,8 +241,8 @@ int lcrec_indexer_set_segments(int on);
 int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
 float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).
- * Tags: 0 = 3xTF32 split of the input, 1+l = MLP layer l, 20 = fused RQ, 21 = sort/unique,
- * 22 = per-group Sinkhorn.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */
+ * Tags: 0 = operand split of the input, 1+l = MLP layer l, 17 = splits of the tail layers, 20 = fused RQ,
+ * 21 = collision checks, 22 / 23 = per-group Sinkhorn of the first / the later rounds.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */
 int lcrec_profile_enable(int on);
 int lcrec_profile_collect(double* ms, int64_t* calls);
 /* number of kernels this library has launched on the calling process so far */

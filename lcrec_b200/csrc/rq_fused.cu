@@ -43,10 +43,10 @@ __device__ __forceinline__ double block_sum_double(double v, double* scratch) {
 // IPT items per thread share every broadcast codebook load (one LDS.128 feeds 4 * IPT FMAs: with one item per
 // thread the kernel is bound by shared-memory instruction issue, not by the FMA pipe); TRAIN adds the
 // straight-through x_q and the per-level squared errors of the training forward.
-template <int D, int IPT, bool TRAIN>
-__global__ void __launch_bounds__(kRqThreads * IPT, 1) rq_quantize_smem_kernel(const RqArgs a) {
+template <int D, int IPT, bool TRAIN, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) rq_quantize_smem_kernel(const RqArgs a) {
   extern __shared__ __align__(16) float smem_f[];
-  __shared__ double red[kRqThreads * IPT / 32];
+  __shared__ double red[THREADS / 32];
   float* cbs[LCREC_MAX_LEVELS];
   float* nrm[LCREC_MAX_LEVELS];
   {
@@ -354,6 +354,16 @@ static int rq_quantize_tc(const RqArgs& a, int D, cudaStream_t st) {
                bytes_x = sizeof(float) * n, bytes_wh = sizeof(__half) * (size_t)kmax * ldh, bytes_ws = sizeof(float) * kmax;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t total = al(bytes_r) + 2 * al(bytes_h) + al(bytes_s) + al(bytes_x) + 2 * al(bytes_wh) + 2 * al(bytes_ws) + 256;
+  static bool pool_set = false;
+  if (!pool_set) {      // keep the stream-ordered pool's memory between calls (the default threshold returns it at every sync)
+    int dev = 0; cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+    pool_set = true;
+  }
   char* ws = nullptr;
   LC_CUDA(cudaMallocAsync((void**)&ws, total, st));
   char* p = ws;
@@ -395,12 +405,14 @@ static int rq_quantize_tc(const RqArgs& a, int D, cudaStream_t st) {
   return rc;
 }
 
-template <int D, int IPT, bool TRAIN>
+static int g_rq_ipt = 4;      // items per thread of the generation-path kernel (2 or 4; lcrec_rq_set_tc_mode(10 + ipt) for experiments)
+
+template <int D, int IPT, bool TRAIN, int THREADS>
 static int launch_rq_smem_impl(const RqArgs& a, size_t smem, cudaStream_t st) {
   static bool attr = false;
-  auto kern = rq_quantize_smem_kernel<D, IPT, TRAIN>;
+  auto kern = rq_quantize_smem_kernel<D, IPT, TRAIN, THREADS>;
   if (!attr) { LC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); attr = true; }
-  const int threads = kRqThreads * IPT;
+  const int threads = THREADS;
   const int64_t blocks = std::min<int64_t>(ceil_div(a.n, threads * IPT), (int64_t)num_sms());
   kern<<<(unsigned)blocks, threads, smem, st>>>(a);
   LC_LAUNCH_CHECK("rq_quantize_smem_kernel");
@@ -408,9 +420,14 @@ static int launch_rq_smem_impl(const RqArgs& a, size_t smem, cudaStream_t st) {
 }
 template <int D>
 static int launch_rq_smem(const RqArgs& a, size_t smem, cudaStream_t st) {
-  if (a.xq != nullptr || a.sq_err != nullptr) return launch_rq_smem_impl<D, 1, true>(a, smem, st);
-  if constexpr (D <= 32) { if (a.n >= 4096) return launch_rq_smem_impl<D, 2, false>(a, smem, st); }
-  return launch_rq_smem_impl<D, 1, false>(a, smem, st);
+  if (a.xq != nullptr || a.sq_err != nullptr) return launch_rq_smem_impl<D, 1, true, 256>(a, smem, st);
+  if constexpr (D <= 32) {
+    if (a.n >= 4096) {
+      if (g_rq_ipt == 4 && a.n >= 65536) return launch_rq_smem_impl<D, 4, false, 256>(a, smem, st);
+      return launch_rq_smem_impl<D, 2, false, 512>(a, smem, st);
+    }
+  }
+  return launch_rq_smem_impl<D, 1, false, 256>(a, smem, st);
 }
 
 }  // namespace lcrec
@@ -421,6 +438,7 @@ static int g_rq_tc_mode = 1;
 // 0 = never use the tensor-core distance path, 1 (default) = for large codebooks (>= 4096 codes or e_dim >= 128),
 // 2 = whenever the shape allows it (cross-checks)
 extern "C" int lcrec_rq_set_tc_mode(int mode) {
+  if (mode == 12 || mode == 14) { g_rq_ipt = mode - 10; return LCREC_OK; }      // experiment switch: items per thread
   LC_ARG(mode >= 0 && mode <= 2);
   g_rq_tc_mode = mode;
   return LCREC_OK;

@@ -5,8 +5,8 @@ Mirrors ``index/models/layers.py`` of the reference (``MLPLayers`` :7-43, ``acti
 sub-module layout (so ``state_dict`` keys ``mlp_layers.{i}.weight`` ... are interchangeable with
 reference checkpoints), but the arithmetic runs in liblcrec_b200.so:
 
-* inference (no autograd): the whole stack is one ``MlpHandle`` - tcgen05 3xTF32 GEMMs with fused
-  bias + ReLU, activations handed from layer to layer already split; eval-mode BatchNorm is folded
+* inference (no autograd): the whole stack is one ``MlpHandle`` - fp32-accurate split-operand tcgen05 GEMMs with
+  fused bias + ReLU, activations handed from layer to layer already split; eval-mode BatchNorm is folded
   into the weights;
 * training: each ``nn.Linear`` (+ReLU when nothing sits between them) goes through the same GEMM
   kernel inside an autograd Function; BatchNorm / Dropout / non-ReLU activations stay torch modules.

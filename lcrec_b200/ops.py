@@ -69,7 +69,7 @@ def profile_collect() -> dict:
 
 # --------------------------------------------------------------------------- MLP
 class MlpHandle:
-    """Prepared (3xTF32-split) weights of one MLPLayers stack."""
+    """Prepared (hi/lo-split) weights of one MLPLayers stack."""
 
     def __init__(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
                  relu_last: bool = False):

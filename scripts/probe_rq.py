@@ -12,7 +12,15 @@ def t(fn, it=5):
     for _ in range(it): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / it
-for n, d, ks in ((1_000_000, 32, [256] * 4), (262144, 256, [8192] * 4)):
+z = torch.randn(1_000_000, 32, device=dev, generator=g)
+cbs = [torch.randn(256, 32, device=dev, generator=g) * 0.7 * 0.6 ** l for l in range(4)]
+ops.rq_set_tc_mode(0)
+for ipt in (2, 4, 2, 4):
+    ops.rq_set_tc_mode(10 + ipt)
+    ms = t(lambda: ops.rq_quantize(z, cbs, resid_level=3))
+    print(json.dumps({"simt_items_per_thread": ipt, "ms_per_1M": round(ms, 3)}), flush=True)
+ops.rq_set_tc_mode(12); ops.rq_set_tc_mode(1)
+for n, d, ks in ((1_000_000, 32, [256] * 4),):
     z = torch.randn(n, d, device=dev, generator=g)
     cbs = [torch.randn(k, d, device=dev, generator=g) * 0.7 * 0.6 ** l for l, k in enumerate(ks)]
     out = {"n": n, "e_dim": d, "codes": ks}
