@@ -88,6 +88,13 @@ int64_t lcrec_linear_backward_workspace_bytes(int64_t n_rows, int k_in, int n_ou
 int lcrec_linear_backward(const float* x, const float* w, const float* y_relu, const float* gy, int64_t n_rows,
                           int k_in, int n_out, float* gx, float* gw, float* gb, void* ws, int64_t ws_bytes,
                           void* stream);
+/* Backward of a whole MLPLayers stack in one call: acts[l] = output of layer l as returned by lcrec_mlp_forward(acts),
+ * gy = gradient w.r.t. the stack's output; gw[l] (dims[l+1] x dims[l]) and gb[l] receive the parameter gradients,
+ * gx (nullable) the input gradient.  weights[l]: the fp32 weights the forward used. */
+int64_t lcrec_mlp_backward_workspace_bytes(const lcrec_mlp_t* mlp, int64_t n_rows);
+int lcrec_mlp_backward(lcrec_mlp_t* mlp, const float* const* weights, const float* x, const float* const* acts,
+                       const float* gy, int64_t n_rows, float* gx, float* const* gw, float* const* gb, void* ws,
+                       int64_t ws_bytes, void* stream);
 
 /* ---- a3/a4/a7/a9: ResidualVectorQuantizer.forward, argmin branch ------------------------
  * (index/models/rq.py:39-56, vq.py:63-75,87-99).  One fused pass over all L levels:

@@ -51,6 +51,8 @@ SIGNATURES = {
                                              C.c_int, C.c_int, C.c_int, vp, vp, i64, vp]),
     "lcrec_linear_backward_workspace_bytes": (i64, [i64, C.c_int, C.c_int]),
     "lcrec_linear_backward": (C.c_int, [vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, vp, i64, vp]),
+    "lcrec_mlp_backward_workspace_bytes": (i64, [vp, i64]),
+    "lcrec_mlp_backward": (C.c_int, [vp, pp, vp, pp, vp, i64, vp, pp, pp, vp, i64, vp]),
     "lcrec_rq_set_tc_mode": (C.c_int, [C.c_int]),
     "lcrec_sinkhorn_groups_ex": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, i64, i64, i64, f64, C.c_int, vp, C.c_int,
                                            C.c_int, C.c_int, C.c_int, vp, vp, i64, vp]),

@@ -882,3 +882,43 @@ extern "C" int lcrec_linear_backward(const float* x, const float* w, const float
   }
   return LCREC_OK;
 }
+
+// ====================================================================== backward of a whole MLP stack
+// acts[l] = output of layer l (fp32, ReLU applied for l < n_layers - 1, exactly what lcrec_mlp_forward returns through
+// `acts`); gy = gradient w.r.t. the last layer's output.  gw[l] / gb[l] receive the parameter gradients, gx (nullable)
+// the gradient w.r.t. the input.  One native loop over lcrec_linear_backward (no per-layer host round trip).
+extern "C" int64_t lcrec_mlp_backward_workspace_bytes(const lcrec_mlp_t* m, int64_t n_rows) {
+  if (!m || n_rows < 0) return -1;
+  int64_t sub = 0; int widest = 0;
+  for (int l = 0; l < m->n_layers; ++l) {
+    sub = std::max(sub, lcrec_linear_backward_workspace_bytes(n_rows, m->dims[l], m->dims[l + 1]));
+    widest = std::max(widest, m->dims[l]);
+  }
+  return sub + 2 * arena_need(sizeof(float) * n_rows * widest) + 1024;
+}
+
+extern "C" int lcrec_mlp_backward(lcrec_mlp_t* m, const float* const* weights, const float* x, const float* const* acts,
+                                  const float* gy, int64_t n_rows, float* gx, float* const* gw, float* const* gb, void* ws,
+                                  int64_t ws_bytes, void* stream) {
+  LC_ARG(m && weights && acts && gy && gw && n_rows >= 0);
+  LC_ARG(x != nullptr || n_rows == 0);
+  int widest = 0;
+  for (int l = 0; l < m->n_layers; ++l) widest = std::max(widest, m->dims[l]);
+  Arena ar(ws, ws_bytes);
+  float* gbuf[2] = {ar.take<float>(n_rows * widest), ar.take<float>(n_rows * widest)};
+  int64_t sub_bytes = 0;
+  for (int l = 0; l < m->n_layers; ++l) sub_bytes = std::max(sub_bytes, lcrec_linear_backward_workspace_bytes(n_rows, m->dims[l], m->dims[l + 1]));
+  char* sub = ar.take<char>(sub_bytes);
+  if (!ar.ok()) { set_error("mlp_backward: workspace too small"); return LCREC_ERR_NOMEM; }
+  const float* g = gy;
+  for (int l = m->n_layers - 1; l >= 0; --l) {
+    const bool relu = (l != m->n_layers - 1) || m->relu_last;
+    const float* in = l == 0 ? x : acts[l - 1];
+    float* g_prev = l == 0 ? gx : gbuf[l & 1];
+    LC_ARG(weights[l] != nullptr && acts[l] != nullptr && gw[l] != nullptr);
+    LC_TRY(lcrec_linear_backward(in, weights[l], relu ? acts[l] : nullptr, g, n_rows, m->dims[l], m->dims[l + 1], g_prev, gw[l],
+                                 gb ? gb[l] : nullptr, sub, sub_bytes, stream));
+    g = g_prev;
+  }
+  return LCREC_OK;
+}

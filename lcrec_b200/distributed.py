@@ -141,7 +141,18 @@ def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank
                            group=None, n_codes=None):
     """Sharded ``generate_indices``: returns (codes of this rank's items, stats).  Collective: every
     rank of ``group`` must call it."""
+    import os
+    timing = os.environ.get("LCREC_DIST_TIMING") == "1" and x_local.is_cuda
+    marks = []
+
+    def mark(name):
+        if timing:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+    mark("start")
     codes_local, resid_local = backend.pass0(x_local)
+    mark("pass0")
     n_codes = n_codes or getattr(backend, "n_codes")
     if plan.world == 1:
         codes = codes_local.contiguous()
@@ -159,12 +170,15 @@ def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
     send_splits, recv_splits = send_counts.tolist(), recv_counts.tolist()
+    mark("partition+counts")
     n_mine = int(sum(recv_splits))
     sub_codes = torch.empty((n_mine, codes_local.shape[1]), dtype=codes_local.dtype, device=codes_local.device)
     sub_resid = torch.empty((n_mine, resid_local.shape[1]), dtype=resid_local.dtype, device=resid_local.device)
     dist.all_to_all_single(sub_codes, codes_local.index_select(0, order).contiguous(), recv_splits, send_splits, group=group)
     dist.all_to_all_single(sub_resid, resid_local.index_select(0, order).contiguous(), recv_splits, send_splits, group=group)
+    mark("exchange")
     st = resolve_rounds(backend, sub_codes, sub_resid, max_rounds)
+    mark("rounds")
     # the owners return the resolved last-level codes along the same routes
     back = torch.empty((codes_local.shape[0],), dtype=codes_local.dtype, device=codes_local.device)
     dist.all_to_all_single(back, sub_codes[:, last].contiguous(), send_splits, recv_splits, group=group)
@@ -177,6 +191,11 @@ def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     n_unique, g1, r1, rows = [int(v) for v in agg.tolist()]
     rounds, max_mult = [int(v) for v in mx.tolist()]
+    mark("return+stats")
+    if timing and rank == 0:
+        torch.cuda.synchronize()
+        import sys
+        print("dist timing (ms): " + ", ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.2f}" for a, b in zip(marks[:-1], marks[1:])), file=sys.stderr)
     stats = {"rounds": rounds, "n_unique": n_unique, "groups_round1": g1, "rows_round1": r1, "sinkhorn_rows": rows,
              "max_multiplicity": max_mult, "collision_rate": (plan.n_total - n_unique) / max(plan.n_total, 1),
              "bucket_items_this_rank": n_mine}

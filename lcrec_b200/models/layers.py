@@ -58,6 +58,30 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+class _MlpFn(torch.autograd.Function):
+    """A whole Linear/ReLU stack as ONE autograd node: forward = lcrec_mlp_forward (activations kept for the backward),
+    backward = lcrec_mlp_backward (one native loop over the layers).  Used in training when nothing but ReLU sits
+    between the Linear layers (no BatchNorm, no active Dropout)."""
+
+    @staticmethod
+    def forward(ctx, x, handle, n_layers, *params):
+        y, acts = handle.forward(x, want_acts=True)
+        ctx.handle = handle
+        ctx.save_for_backward(x, *acts)
+        ctx.has_bias = [params[2 * i + 1] is not None for i in range(n_layers)]
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, *acts = ctx.saved_tensors
+        gx, gws, gbs = ctx.handle.backward(x, acts, gy, need_gx=ctx.needs_input_grad[0])
+        grads = []
+        for i, (gw, gb) in enumerate(zip(gws, gbs)):
+            grads.append(gw if ctx.needs_input_grad[3 + 2 * i] else None)
+            grads.append(gb if (ctx.has_bias[i] and ctx.needs_input_grad[4 + 2 * i]) else None)
+        return (gx, None, None, *grads)
+
+
 class MLPLayers(nn.Module):
     def __init__(self, layers, dropout=0.0, activation="relu", bn=False):
         super().__init__()
@@ -148,11 +172,32 @@ class MLPLayers(nn.Module):
             self._handle_key = key
         return self._handle
 
+    def _stack_ok(self) -> bool:
+        """Training with autograd, and the stack is Linear(+ReLU) only: one fused autograd node serves it."""
+        blocks = self._blocks()
+        for i, (dp, lin, bn, act) in enumerate(blocks):
+            last = i == len(blocks) - 1
+            if bn is not None or (self.training and dp.p > 0) or lin.bias is None:
+                return False
+            if (not last and not isinstance(act, nn.ReLU)) or (last and act is not None):
+                return False
+            if lin.out_features % 4 != 0 or lin.in_features % 4 != 0:
+                return False
+        return True
+
     def forward(self, input_feature):
         if not input_feature.is_cuda:
             raise RuntimeError("lcrec_b200.MLPLayers runs on CUDA only (no CPU fallback)")
         if self._fused_ok():
             return self._get_handle().forward(input_feature)
+        if self._stack_ok():
+            handle = self._get_handle()
+            params = []
+            for dp, lin, bn, act in self._blocks():
+                params += [lin.weight, lin.bias]
+            lead = input_feature.shape[:-1]
+            y = _MlpFn.apply(input_feature.reshape(-1, input_feature.shape[-1]), handle, len(params) // 2, *params)
+            return y.reshape(*lead, y.shape[-1])
         x = input_feature
         blocks = self._blocks()
         for i, (dp, lin, bn, act) in enumerate(blocks):

@@ -133,6 +133,25 @@ class MlpHandle:
         y = y.reshape(*x.shape[:-1], self.dims[-1])
         return (y, acts) if want_acts else y
 
+    def backward(self, x: torch.Tensor, acts: Sequence[torch.Tensor], gy: torch.Tensor, need_gx: bool = True):
+        """Gradients of the whole stack (lcrec_mlp_backward): returns (gx or None, [gw_l], [gb_l]).  ``acts`` as returned
+        by ``forward(x, want_acts=True)``; the weights are the ones of the last ``update`` / construction."""
+        _need_cuda(x, gy)
+        x2 = _f32c(x.reshape(-1, self.dims[0]))
+        g2 = _f32c(gy.reshape(-1, self.dims[-1]))
+        n = x2.shape[0]
+        dev = x2.device
+        gx = torch.empty((n, self.dims[0]), dtype=torch.float32, device=dev) if need_gx else None
+        gws = [torch.empty((fo, fi), dtype=torch.float32, device=dev) for fi, fo in zip(self.dims[:-1], self.dims[1:])]
+        gbs = [torch.empty((fo,), dtype=torch.float32, device=dev) for fo in self.dims[1:]]
+        ws = _ws(self.lib.lcrec_mlp_backward_workspace_bytes(self.handle, n), dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.lcrec_mlp_backward(self.handle, _lib.ptr_array([w.data_ptr() for w in self._keep]), _p(x2),
+                                                   _lib.ptr_array([a.data_ptr() for a in acts]), _p(g2), n, _p(gx),
+                                                   _lib.ptr_array([g.data_ptr() for g in gws]),
+                                                   _lib.ptr_array([g.data_ptr() for g in gbs]), _p(ws), ws.numel(), _stream(x2)))
+        return (None if gx is None else gx.reshape(x.shape)), gws, gbs
+
     def __del__(self):
         try:
             if self.handle:

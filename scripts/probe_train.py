@@ -56,3 +56,36 @@ for name, fn in (("ours", step_ours), ("torch_fp32", step_ref)):
     ms = (time.perf_counter() - t0) / steps * 1e3
     out[name + "_ms_per_step"] = round(ms, 3); out[name + "_items_per_s"] = round(B / ms * 1e3)
 print(json.dumps(out))
+
+# ---- section breakdown of our step (synchronised sections: sums exceed the pipelined step time)
+import collections
+acc = collections.OrderedDict()
+def sec(name, t0):
+    torch.cuda.synchronize(); acc[name] = acc.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+for i in range(10):
+    xb = x[(i % 4) * B:(i % 4 + 1) * B]
+    torch.cuda.synchronize(); t0 = time.perf_counter(); opt.zero_grad(); sec("zero_grad", t0)
+    t0 = time.perf_counter(); z = m.encoder(xb); sec("encoder_fwd", t0)
+    t0 = time.perf_counter(); xq, rq_loss, idx = m.rq(z, use_sk=True); sec("rq_fwd", t0)
+    t0 = time.perf_counter(); out = m.decoder(xq); sec("decoder_fwd", t0)
+    t0 = time.perf_counter(); loss, rec = m.compute_loss(out, rq_loss, xs=xb); sec("loss", t0)
+    t0 = time.perf_counter(); loss.backward(); sec("backward", t0)
+    t0 = time.perf_counter(); torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0); sec("clip", t0)
+    t0 = time.perf_counter(); opt.step(); sec("optimizer", t0)
+print(json.dumps({k: round(v / 10, 3) for k, v in acc.items()}))
+
+# ---- GPU time of the native MLP forward / backward calls alone
+from lcrec_b200 import ops
+h = m.encoder._get_handle()
+xb = x[:B]
+y, acts = h.forward(xb, want_acts=True)
+gy = torch.randn_like(y)
+for name, fn in (("encoder_mlp_forward", lambda: h.forward(xb, want_acts=True)), ("encoder_mlp_backward", lambda: h.backward(xb, acts, gy, need_gx=False)),
+                 ("encoder_weight_update", lambda: h.update(h._keep, h._keepb))):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record()
+    for _ in range(10): fn()
+    e1.record(); host_ms = (time.perf_counter() - t0) / 10 * 1e3; torch.cuda.synchronize()
+    print(json.dumps({name + "_gpu_ms": round(e0.elapsed_time(e1) / 10, 3), "host_issue_ms": round(host_ms, 3)}))
