@@ -91,6 +91,35 @@ def test_index_json_is_byte_identical_to_reference(golden, tmp_path):
     assert json.loads(out.read_text())["0"][0].startswith("<a_")
 
 
+def test_index_json_satisfies_the_downstream_consumer(golden, tmp_path):
+    """The file is read by BaseDataset (reference data.py:38-89): json.load -> {str(item): [tok_0..tok_{L-1}]};
+    get_new_tokens = sorted set of all tokens (fed to tokenizer.add_tokens), get_all_items = set of "".join(tokens)
+    (must be one entry per item when the table is collision free), get_prefix_allowed_tokens_fn groups tokens by
+    level.  Restated here on our writer's output."""
+    import re
+    g = golden("small_model")
+    codes = np.asarray(g["script_codes_final"])
+    out = tmp_path / "y.index.json"
+    G.write_index_json(codes, str(out))
+    indices = json.loads(out.read_text())
+    assert list(indices.keys()) == [str(i) for i in range(codes.shape[0])]            # int keys serialised as strings, item order
+    L = codes.shape[1]
+    pat = [re.compile(r"^<%s_(\d+)>$" % "abcde"[l]) for l in range(L)]
+    new_tokens, all_items, by_level = set(), set(), {}
+    for idx, (item, toks) in enumerate(indices.items()):
+        assert len(toks) == L
+        for l, t in enumerate(toks):
+            m = pat[l].match(t)
+            assert m and int(m.group(1)) == int(codes[idx, l])                          # level letter + code value round-trip
+            new_tokens.add(t)
+            by_level.setdefault(l, set()).add(t)
+        all_items.add("".join(toks))
+    assert sorted(new_tokens) == sorted(set(t for toks in indices.values() for t in toks))
+    assert len(all_items) == len({tuple(r) for r in codes.tolist()})                   # one string per distinct code tuple
+    assert all(len(by_level[l]) == len(set(codes[:, l].tolist())) for l in range(L))  # allowed-token sets per level
+    assert not (set.intersection(*[by_level[l] for l in range(L)]) if L > 1 else set())   # levels never share a token
+
+
 def test_schedulers_match_transformers():
     tr = pytest.importorskip("transformers")
     for make_ours, make_ref in [
