@@ -50,17 +50,20 @@ struct PairArgs {
   long long* trace;   // measurement only: clock64 stamps of cluster 0's leader CTA (6 roles x 512 events x 4)
 };
 
-template <int BK, int STAGES>
+template <int BK, int STAGES, int TILE_N = 256>
 struct PairCfg {
   static constexpr int ROW_BYTES = BK * 2;
-  static constexpr int OP_BYTES = kHalfM * ROW_BYTES;            // one 128-row operand slab
-  static constexpr int STAGE_BYTES = 4 * OP_BYTES;               // A_hi, A_lo, B_hi, B_lo (this CTA's halves)
+  static constexpr int A_BYTES = kHalfM * ROW_BYTES;             // this CTA's 128 A rows (one of hi / lo)
+  static constexpr int B_BYTES = (TILE_N / 2) * ROW_BYTES;       // this CTA's half of the B rows (one of hi / lo)
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // A_hi, A_lo, B_hi, B_lo
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 8 * kStageWords * 4 + 1024 /* xch */ + 1024 /* alignment */;
   static constexpr uint32_t SBO = 8 * ROW_BYTES;
   static constexpr uint32_t LAYOUT = ROW_BYTES == 128 ? 2u : 4u;
   static constexpr int KB_PER_CHUNK = kGroup / BK;
   static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "a K block spans one 128 B or 64 B swizzle row");
   static_assert(kGroup % BK == 0, "a chunk is a whole number of K blocks");
+  static_assert(TILE_N == 256 || TILE_N == 128 || TILE_N == 64, "tile widths");
+  static_assert(B_BYTES % 1024 == 0, "operand slabs start on swizzle-atom boundaries");
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
@@ -69,12 +72,13 @@ __device__ __forceinline__ void stamp(long long* trace, int role, uint32_t idx, 
   if (trace != nullptr && idx < 512u) trace[((size_t)role * 512 + idx) * 4 + slot] = clock64();
 }
 
-template <int BK, int STAGES, bool ARGMIN>
+template <int BK, int STAGES, bool ARGMIN, int TILE_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                    const PairArgs args) {
-  using C = PairCfg<BK, STAGES>;
+  using C = PairCfg<BK, STAGES, TILE_N>;
+  static_assert(!ARGMIN || TILE_N == 256, "the argmin epilogue walks 256-wide code tiles");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;      // same offset in both CTAs of the pair
@@ -128,7 +132,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         const int tile_n = ARGMIN ? nn : (int)(unit % args.tiles_n);
         const int64_t tile_m = ARGMIN ? unit : unit / args.tiles_n;
         const int row0 = (int)(tile_m * 256 + rank * kHalfM);
-        const int col0 = tile_n * kTileN + (int)rank * kHalfM;
+        const int col0 = tile_n * TILE_N + (int)rank * (TILE_N / 2);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
@@ -143,9 +147,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           const uint32_t dst = base + s * C::STAGE_BYTES;
           const uint32_t bar = leader_addr(full_bar(s));
           tma_load_2d_2sm(dst, &map_ahi, bar, kb * BK, row0);
-          tma_load_2d_2sm(dst + C::OP_BYTES, &map_alo, bar, kb * BK, row0);
-          tma_load_2d_2sm(dst + 2 * C::OP_BYTES, &map_bhi, bar, kb * BK, col0);
-          tma_load_2d_2sm(dst + 3 * C::OP_BYTES, &map_blo, bar, kb * BK, col0);
+          tma_load_2d_2sm(dst + C::A_BYTES, &map_alo, bar, kb * BK, row0);
+          tma_load_2d_2sm(dst + 2 * C::A_BYTES, &map_bhi, bar, kb * BK, col0);
+          tma_load_2d_2sm(dst + 2 * C::A_BYTES + C::B_BYTES, &map_blo, bar, kb * BK, col0);
         }
       }
     }
@@ -154,7 +158,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     // ------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(256, kTileN, 0);
+      constexpr uint32_t idesc = umma_idesc(256, TILE_N, 0);
       uint32_t it = 0, cc = 0;
       for (int64_t unit = cluster_id; unit < n_units; unit += n_clusters)
       for (int nn = 0; nn < inner; ++nn) {
@@ -165,7 +169,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           mbar_wait(tempty_bar(b), ((cc >> 1) & 1u) ^ 1u);
           stamp(trace, 2, cc, 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + b * kTileN;
+          const uint32_t d_tmem = tmem_base + b * TILE_N;
           const int kb_end = min(nkb, kb + C::KB_PER_CHUNK);
           bool first = true;
           for (; kb < kb_end; ++kb, ++it) {
@@ -177,9 +181,9 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             tc_fence_after();
             const uint32_t a_hi = base + s * C::STAGE_BYTES;
             const uint64_t d_ahi = umma_smem_desc(a_hi, C::SBO, C::LAYOUT);
-            const uint64_t d_alo = umma_smem_desc(a_hi + C::OP_BYTES, C::SBO, C::LAYOUT);
-            const uint64_t d_bhi = umma_smem_desc(a_hi + 2 * C::OP_BYTES, C::SBO, C::LAYOUT);
-            const uint64_t d_blo = umma_smem_desc(a_hi + 3 * C::OP_BYTES, C::SBO, C::LAYOUT);
+            const uint64_t d_alo = umma_smem_desc(a_hi + C::A_BYTES, C::SBO, C::LAYOUT);
+            const uint64_t d_bhi = umma_smem_desc(a_hi + 2 * C::A_BYTES, C::SBO, C::LAYOUT);
+            const uint64_t d_blo = umma_smem_desc(a_hi + 2 * C::A_BYTES + C::B_BYTES, C::SBO, C::LAYOUT);
             if (!(args.debug & 2)) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -201,7 +205,7 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
   } else if (warp < 8) {
     // ------------------------------------------------------------ fold + epilogue warps (both CTAs)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    constexpr int NCOL = kTileN / 2;                  // 128 columns per thread = half an output scale group
+    constexpr int NCOL = TILE_N / 2;                  // columns per thread (128 at full width) = half an output scale group
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     const int half = warp >> 2;                       // column half
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * NCOL);
@@ -227,23 +231,31 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         mbar_wait(tfull_bar(b), (cc >> 1) & 1u);
         if (warp == 0 && lane == 0) stamp(trace, 3, cc, 1);
         tc_fence_after();
+        if constexpr (NCOL >= 64) {
 #pragma unroll
-        for (int j = 0; j < NCOL; j += 64) {      // two TMEM loads in flight per wait
-          uint32_t v0[32], v1[32];
-          tmem_ld32(t_lane + b * kTileN + (uint32_t)j, v0);
-          tmem_ld32(t_lane + b * kTileN + (uint32_t)(j + 32), v1);
+          for (int j = 0; j < NCOL; j += 64) {      // two TMEM loads in flight per wait
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_lane + b * TILE_N + (uint32_t)j, v0);
+            tmem_ld32(t_lane + b * TILE_N + (uint32_t)(j + 32), v1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j + i] = fmaf(__uint_as_float(v0[i]), sc, acc[j + i]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j + 32 + i] = fmaf(__uint_as_float(v1[i]), sc, acc[j + 32 + i]);
+          }
+        } else {
+          uint32_t v0[32];
+          tmem_ld32(t_lane + b * TILE_N, v0);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j + i] = fmaf(__uint_as_float(v0[i]), sc, acc[j + i]);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j + 32 + i] = fmaf(__uint_as_float(v1[i]), sc, acc[j + 32 + i]);
+          for (int i = 0; i < 32; ++i) acc[i] = fmaf(__uint_as_float(v0[i]), sc, acc[i]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader[b]);
         if (warp == 0 && lane == 0) stamp(trace, 3, cc, 2);
       }
-      const int col_base = tile_n * kTileN + half * NCOL;
+      const int col_base = tile_n * TILE_N + half * NCOL;
       if constexpr (ARGMIN) {
         // ---- distance + first-argmin epilogue (vq.py:71-75): d = (|r|^2 + |c|^2) - 2 r.c in fp32, strict < keeps the lowest
         // index inside the thread's ascending column scan; the two column halves of a row are merged at the end
@@ -447,10 +459,10 @@ __global__ void __launch_bounds__(256) split_groups_kernel(const float* __restri
 
 int g_pair_cluster_cap = 0;     // > 0: persistent grid limited to this many CTA pairs (leaves SMs to concurrent kernels)
 
-template <int BK, int STAGES, bool ARGMIN>
+template <int BK, int STAGES, bool ARGMIN, int TILE_N = 256>
 int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
-  using C = PairCfg<BK, STAGES>;
-  auto kern = linear_pair_kernel<BK, STAGES, ARGMIN>;
+  using C = PairCfg<BK, STAGES, TILE_N>;
+  auto kern = linear_pair_kernel<BK, STAGES, ARGMIN, TILE_N>;
   static bool attr_set = false;
   static int max_clusters = 0;
   if (!attr_set) {
@@ -468,11 +480,11 @@ int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   LC_TRY(make_map(&ma_hi, p.a.hi, p.n_rows, p.k, p.a.ld, BK, kHalfM, 2));
   LC_TRY(make_map(&ma_lo, p.a.lo, p.n_rows, p.k, p.a.ld, BK, kHalfM, 2));
-  LC_TRY(make_map(&mb_hi, p.w_hi, p.n_out, p.k, p.ldw, BK, kHalfM, 2));
-  LC_TRY(make_map(&mb_lo, p.w_lo, p.n_out, p.k, p.ldw, BK, kHalfM, 2));
+  LC_TRY(make_map(&mb_hi, p.w_hi, p.n_out, p.k, p.ldw, BK, TILE_N / 2, 2));
+  LC_TRY(make_map(&mb_lo, p.w_lo, p.n_out, p.k, p.ldw, BK, TILE_N / 2, 2));
   PairArgs a{};
   a.n_rows = p.n_rows; a.n_out = p.n_out; a.k = p.k;
-  a.tiles_n = p.n_out / kTileN;
+  a.tiles_n = p.n_out / TILE_N;
   a.n_tiles = ceil_div(p.n_rows, 256) * a.tiles_n;
   a.a_inv_scale = p.a.inv_scale; a.ld_ascale = p.a.ld_scale;
   a.w_inv_scale = p.w_inv_scale; a.bias = p.bias; a.relu = p.relu;
@@ -492,8 +504,9 @@ int launch_pair_cfg(const PairProblem& p, cudaStream_t st) {
 
 void set_pair_cluster_cap(int cap) { g_pair_cluster_cap = cap; }
 
+// full-width tiles for n_out a multiple of 256; one narrower tile for the 128- and 64-wide tail layers
 bool linear_pair_supported(int k, int n_out, int group) {
-  return group == kGroup && n_out >= kTileN && n_out % kTileN == 0 && k >= 64 && k % 8 == 0;
+  return group == kGroup && ((n_out >= kTileN && n_out % kTileN == 0) || n_out == 128 || n_out == 64) && k >= 64 && k % 8 == 0;
 }
 bool argmin_pair_supported(int k, int n_out) { return n_out >= kTileN && n_out % kTileN == 0 && k >= 8 && k % 8 == 0; }
 
@@ -508,6 +521,8 @@ int launch_linear_pair(const PairProblem& p, cudaStream_t st) {
     set_error("linear_pair: bias / channel scales must be 16-byte aligned");
     return LCREC_ERR_ARG;
   }
+  if (p.n_out == 128) return launch_pair_cfg<64, 4, false, 128>(p, st);
+  if (p.n_out == 64) return launch_pair_cfg<64, 4, false, 64>(p, st);
   if (p.debug & 4) return launch_pair_cfg<32, 6, false>(p, st);
   return launch_pair_cfg<64, 3, false>(p, st);
 }

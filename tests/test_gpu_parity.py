@@ -39,7 +39,8 @@ def load_small(golden, name):
 
 # ------------------------------------------------------------------ a2: linear / MLP
 @pytest.mark.parametrize("n,k,m", [(1, 32, 32), (128, 64, 64), (200, 96, 64), (300, 100, 48), (257, 256, 256),
-                                   (1000, 512, 512), (513, 4096, 2048), (640, 16, 96), (77, 200, 256), (40000, 1024, 512)])
+                                   (1000, 512, 512), (513, 4096, 2048), (640, 16, 96), (77, 200, 256), (40000, 1024, 512),
+                                   (300, 256, 128), (70000, 128, 64), (129, 72, 128)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_linear_matches_fp64(n, k, m, relu):
     g = torch.Generator(device=DEV).manual_seed(n * 7 + k)
@@ -50,8 +51,8 @@ def test_linear_matches_fp64(n, k, m, relu):
     if relu:
         ref = ref.clamp_min(0)
     variants = [0, 1, 2, 3]           # tile variant x operand encoding (tf32 x3 / f16 x3)
-    if m % 256 == 0 and k >= 64:
-        variants += [6, 7]            # CTA-pair kernel (cta_group::2, group-scaled operands), two stage shapes
+    if (m % 256 == 0 or m in (128, 64)) and k >= 64:
+        variants += [6, 7]            # CTA-pair kernel (cta_group::2, group-scaled operands; 256 / 128 / 64 wide tiles)
     for variant in variants:
         y = ops.linear_forward(x, w, b, relu, variant=variant)
         scale = (x.double().abs() @ w.double().abs().t()).mean().item() + 1e-30
