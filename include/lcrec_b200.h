@@ -110,7 +110,8 @@ int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_levels, const 
                       float* xq, float* resid_last, double* sq_err, void* stream);
 /* Kernel choice of lcrec_rq_quantize: 0 = never the tensor-core distance path, 1 (default) = tensor cores (CTA-pair
  * tcgen05 GEMM with a distance + argmin epilogue, fp32-accurate split operands) for large codebooks (>= 4096 codes or
- * e_dim >= 128; code counts multiples of 256), 2 = whenever the shape allows it (cross-checks). */
+ * e_dim >= 128) and, from 4096 rows on, for e_dim 16 / 32 / 64 (code counts multiples of 256 in all cases; other shapes
+ * and smaller batches: SIMT kernels), 2 = whenever the shape allows it (cross-checks). */
 int lcrec_rq_set_tc_mode(int mode);
 
 /* ---- a4: distances only (index/models/vq.py:71-73), (n, K) fp32 ------------------------ */
