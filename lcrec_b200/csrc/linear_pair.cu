@@ -538,6 +538,7 @@ int launch_argmin_pair(const PairProblem& p, cudaStream_t st) {
     set_error("argmin_pair: code norms / scales must be 16-byte aligned");
     return LCREC_ERR_ARG;
   }
+  if (p.k <= 32) return launch_pair_cfg<32, 6, true>(p, st);      // e_dim <= 32: one 64-byte K block, no zero-padded half
   return launch_pair_cfg<64, 3, true>(p, st);
 }
 
