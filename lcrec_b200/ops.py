@@ -164,9 +164,13 @@ class MlpHandle:
 def linear_forward(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], relu: bool,
                    acc_chunk: int = 64, variant: Optional[int] = None) -> torch.Tensor:
     """relu?(x @ w.T + b) with the split-operand tcgen05 kernel (nn.Linear, layers.py:23).
-    variant: bit 0 = alternative tile, bit 1 = f16 x3 engine (default: the module-wide DEFAULT_ENGINE)."""
+    variant: bit 0 = alternative tile, bit 1 = f16 x3 engine, bits 1+2 (6) = CTA-pair kernel; default: the module-wide
+    DEFAULT_ENGINE, on the pair kernel where the shape allows."""
     if variant is None:
         variant = 2 * DEFAULT_ENGINE
+        m_, k_ = int(w.shape[0]), int(w.shape[1])
+        if DEFAULT_ENGINE == 1 and (m_ % 256 == 0 or m_ in (128, 64)) and k_ >= 64 and k_ % 8 == 0:
+            variant = 6                      # CTA-pair kernel (same rule as linear_pair_supported in csrc/linear_pair.cu)
     _need_cuda(x, w)
     lib = _lib.load()
     x2, w2 = _f32c(x.reshape(-1, w.shape[1])), _f32c(w)
