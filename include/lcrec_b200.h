@@ -248,6 +248,33 @@ int lcrec_indexer_resolve(lcrec_indexer_t* ix, int64_t* codes, const float* resi
 int lcrec_indexer_set_segments(int on);
 int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
 float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */
+/* ---- f3: EMA codebook variant (index_improve/models/vq.py) ----------------------------------
+ * lcrec_ema_update: the `self.training and use_ema` block of the improved VectorQuantizer.forward
+ * (index_improve/models/vq.py:146-187) in place on the module's buffers: per-code counts of `indices` (n,) int64,
+ * cluster_size (K,) <- cluster_size * decay + (1 - decay) * counts, the per-code sums of latent (n, e_dim) in ascending
+ * item order (= CPU index_add_, bit-reproducible, no atomics), ema_w (K, e_dim) <- ema_w * decay + (1 - decay) * sums,
+ * and for codes with cluster_size > epsilon: codebook <- codebook * (1 - r) + ema_w / (cluster_size + epsilon) * r,
+ * r = 1 - decay.  Scalars are rounded to fp32 where the reference's Python doubles meet fp32 tensors.  n < 2^31.
+ * lcrec_codebook_usage: get_codebook_usage (vq.py:205-217) and the dead-code test of _reset_unused_codes
+ * (vq.py:83-87): used_codes (1 int64, device) = #{cs / (sum cs + epsilon) > reset_threshold}; unused_mask (nullable,
+ * K bytes) = usage < reset_threshold.  The replacement vectors of a reset are drawn by the caller (torch RNG). */
+int lcrec_ema_update(const float* latent, const int64_t* indices, int64_t n, int n_codes, int e_dim,
+                     double ema_decay, double epsilon, float* cluster_size, float* ema_w, float* codebook,
+                     void* stream);
+int lcrec_codebook_usage(const float* cluster_size, int n_codes, double epsilon, double reset_threshold,
+                         int64_t* used_codes, uint8_t* unused_mask, void* stream);
+/* ---- f4: embedding producer hand-off (data_process/amazon_text_emb.py:91-96) -----------------
+ * Masked mean pool of a PLM's last hidden state: pooled[b] = sum_t mask[b][t] * hidden[b][t][:] / sum_t mask[b][t]
+ * (hidden (n_seq, seq_len, hidden_dim) of dtype 0 = fp32, 1 = fp16, 2 = bf16, row-major; mask (n_seq, seq_len) int64 as
+ * the tokenizer returns it; accumulation and result in fp32).  out[b * out_stride + c] = (accumulate ? out : 0) + pooled,
+ * then / divide_by if divide_by > 0: the mean over an item's text fields (:96) is `accumulate` on every field after the
+ * first and divide_by = n_fields on the last.  `out` may be rows of the (N, in_dim) fp32 embedding matrix that
+ * lcrec_indexer_run_device reads - no .npy round trip.  Padded positions are not read.  workspace: partial sums when a
+ * small batch is split along the sequence (lcrec_masked_mean_pool_workspace_bytes). */
+int64_t lcrec_masked_mean_pool_workspace_bytes(int64_t n_seq, int64_t seq_len, int hidden_dim);
+int lcrec_masked_mean_pool(const void* hidden, int dtype, const int64_t* mask, int64_t n_seq, int64_t seq_len,
+                           int hidden_dim, float* out, int64_t out_stride, int accumulate, double divide_by,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).
  * Tags: 0 = operand split of the input, 1+l = MLP layer l, 17 = splits of the tail layers, 20 = fused RQ,
  * 21 = collision checks, 22 / 23 = per-group Sinkhorn of the first / the later rounds.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */

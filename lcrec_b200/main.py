@@ -13,8 +13,8 @@ from .models.rqvae import RQVAE
 from .trainer import Trainer
 
 
-def parse_args(argv=None):
-    p = argparse.ArgumentParser(description="Index")
+def build_parser(description="Index"):
+    p = argparse.ArgumentParser(description=description)
     p.add_argument("--lr", type=float, default=1e-3)
     p.add_argument("--epochs", type=int, default=5000)
     p.add_argument("--batch_size", type=int, default=2048)
@@ -40,7 +40,11 @@ def parse_args(argv=None):
     p.add_argument("--layers", type=int, nargs="+", default=[2048, 1024, 512, 256, 128, 64])
     p.add_argument("--save_limit", type=int, default=5)
     p.add_argument("--ckpt_dir", type=str, default="")
-    return p.parse_args(argv)
+    return p
+
+
+def parse_args(argv=None):
+    return build_parser().parse_args(argv)
 
 
 def main(argv=None):

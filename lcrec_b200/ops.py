@@ -253,6 +253,74 @@ def vq_distances(r: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# --------------------------------------------------------------------------- EMA codebook variant
+def _inplace_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous fp32 tensor (it is updated in place)")
+    return t
+
+
+def ema_update(latent: torch.Tensor, indices: torch.Tensor, cluster_size: torch.Tensor, ema_w: torch.Tensor,
+               codebook: torch.Tensor, ema_decay: float, epsilon: float) -> None:
+    """EMA step of index_improve/models/vq.py:146-187, in place on (cluster_size, ema_w, codebook)."""
+    _need_cuda(latent, indices, cluster_size, ema_w, codebook)
+    lib = _lib.load()
+    k, d = codebook.shape
+    lat = _f32c(latent.reshape(-1, d))
+    idx = indices.detach().reshape(-1).to(torch.int64).contiguous()
+    if idx.shape[0] != lat.shape[0]:
+        raise RuntimeError("ema_update: one index per latent row expected")
+    _inplace_f32(cluster_size, "cluster_size"); _inplace_f32(ema_w, "ema_w"); _inplace_f32(codebook, "codebook")
+    with torch.cuda.device(lat.device):
+        _lib.check(lib.lcrec_ema_update(_p(lat), _p(idx), lat.shape[0], k, d, float(ema_decay), float(epsilon),
+                                        _p(cluster_size), _p(ema_w), _p(codebook), _stream(lat)))
+
+
+def codebook_usage(cluster_size: torch.Tensor, epsilon: float, reset_threshold: float, want_unused: bool = False):
+    """(used_codes, unused_mask or None) of index_improve/models/vq.py:205-217 / :83-87."""
+    _need_cuda(cluster_size)
+    lib = _lib.load()
+    cs = _f32c(cluster_size)
+    used = torch.zeros(1, dtype=torch.int64, device=cs.device)
+    mask = torch.empty(cs.shape[0], dtype=torch.uint8, device=cs.device) if want_unused else None
+    with torch.cuda.device(cs.device):
+        _lib.check(lib.lcrec_codebook_usage(_p(cs), cs.shape[0], float(epsilon), float(reset_threshold), _p(used),
+                                            _p(mask), _stream(cs)))
+    return int(used.item()), (mask.bool() if want_unused else None)
+
+
+# --------------------------------------------------------------------------- embedding producer hand-off
+_POOL_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def masked_mean_pool(last_hidden_state: torch.Tensor, attention_mask: torch.Tensor, out: Optional[torch.Tensor] = None,
+                     accumulate: bool = False, divide_by: float = 0.0) -> torch.Tensor:
+    """``(h * mask[..., None]).sum(1) / mask.sum(-1, keepdim=True)`` (data_process/amazon_text_emb.py:91-92) -> fp32
+    (B, H).  ``out``: fp32 rows to write (a view into the embedding matrix; row stride >= H, unit column stride);
+    ``accumulate`` adds to ``out``; ``divide_by`` > 0 divides the result (mean over text fields, :96)."""
+    _need_cuda(last_hidden_state, attention_mask, out)
+    lib = _lib.load()
+    if last_hidden_state.dtype not in _POOL_DTYPES:
+        raise RuntimeError(f"masked_mean_pool: unsupported hidden dtype {last_hidden_state.dtype}")
+    h = last_hidden_state.detach().contiguous()
+    b, t, d = h.shape
+    m = attention_mask.detach().to(torch.int64).contiguous()
+    if m.shape != (b, t):
+        raise RuntimeError("masked_mean_pool: attention_mask must be (batch, seq_len)")
+    if out is None:
+        if accumulate:
+            raise RuntimeError("masked_mean_pool: accumulate needs an existing out")
+        out = torch.empty((b, d), dtype=torch.float32, device=h.device)
+    if out.dtype != torch.float32 or out.shape != (b, d) or (d > 1 and out.stride(1) != 1) or out.device != h.device:
+        raise RuntimeError("masked_mean_pool: out must be fp32 (batch, hidden) with unit column stride on the same device")
+    stride = out.stride(0) if b > 1 else max(d, out.stride(0))
+    ws = _ws(lib.lcrec_masked_mean_pool_workspace_bytes(b, t, d), h.device)
+    with torch.cuda.device(h.device):
+        _lib.check(lib.lcrec_masked_mean_pool(_p(h), _POOL_DTYPES[h.dtype], _p(m), b, t, d, _p(out), stride,
+                                              int(accumulate), float(divide_by), _p(ws), ws.numel(), _stream(h)))
+    return out
+
+
 # --------------------------------------------------------------------------- Sinkhorn
 def center_distances(d: torch.Tensor) -> torch.Tensor:
     """center_distance_for_constraint (vq.py:51-61) followed by .double() (vq.py:78)."""

@@ -91,6 +91,9 @@ class Trainer(object):
         if torch.isnan(loss):
             raise ValueError("Training loss is nan")
 
+    def _model_forward(self, data):
+        return self.model(data)                              # trainer.py:114
+
     def _train_epoch(self, train_data, epoch_idx):
         self.model.train()
         total_loss = 0
@@ -99,7 +102,7 @@ class Trainer(object):
         for data in bar:
             data = data.to(self.device)
             self.optimizer.zero_grad()
-            out, rq_loss, _ = self.model(data)
+            out, rq_loss, _ = self._model_forward(data)
             loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=data)
             self._check_nan(loss)
             loss.backward()
@@ -138,6 +141,10 @@ class Trainer(object):
         return (head + set_color("train loss", "blue") + ": %.4f" % loss + ", " +
                 set_color("reconstruction loss", "blue") + ": %.4f" % recon_loss + "]")
 
+    def _generate_valid_output(self, epoch_idx, seconds, collision_rate):
+        return (set_color("epoch %d evaluating", "green") + " [" + set_color("time", "blue") + ": %.2fs, " +
+                set_color("collision_rate", "blue") + ": %f]") % (epoch_idx, seconds, collision_rate)
+
     def fit(self, data):
         for epoch_idx in range(self.epochs):
             t0 = time()
@@ -153,9 +160,7 @@ class Trainer(object):
             if collision_rate < self.best_collision_rate:
                 self.best_collision_rate = collision_rate
                 self._save_checkpoint(epoch_idx, collision_rate=collision_rate, ckpt_file=self.best_collision_ckpt)
-            self.logger.info((set_color("epoch %d evaluating", "green") + " [" + set_color("time", "blue") +
-                              ": %.2fs, " + set_color("collision_rate", "blue") + ": %f]") %
-                             (epoch_idx, time() - t0, collision_rate))
+            self.logger.info(self._generate_valid_output(epoch_idx, time() - t0, collision_rate))
             ckpt_path = self._save_checkpoint(epoch_idx, collision_rate=collision_rate)
             now_save = (-collision_rate, ckpt_path)
             if len(self.newest_save_queue) < self.save_limit:        # rotation, trainer.py:231-247

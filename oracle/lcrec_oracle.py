@@ -204,6 +204,102 @@ def vq_forward(x: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: fl
 
 
 # --------------------------------------------------------------------------- #
+# f3: index_improve EMA codebook update, usage statistics, dead-code reset
+# --------------------------------------------------------------------------- #
+def _fma32(a, b, c):
+    """fp32 ``fma(a, b, c)``: the product of two fp32 numbers is exact in fp64, so one fp64 add + one rounding to
+    fp32 differs from the fused result only by double rounding (never seen against the golden vectors).  torch's CPU
+    ``add_(t, alpha=s)`` is ``vec::fmadd(t, s, self)`` and the CUDA functor ``a + alpha * b`` contracts to FFMA."""
+    return (np.asarray(a, F32).astype(F64) * np.asarray(b, F32).astype(F64) + np.asarray(c, F32).astype(F64)).astype(F32)
+
+
+@dataclass
+class EmaState:
+    """Buffers of the index_improve ``VectorQuantizer`` (index_improve/models/vq.py:39-42)."""
+    codebook: np.ndarray          # (K, D) fp32  embedding.weight
+    cluster_size: np.ndarray      # (K,)  fp32   _ema_cluster_size
+    ema_w: np.ndarray             # (K, D) fp32  _ema_w
+    step_count: int = 0
+
+
+def ema_update(latent: np.ndarray, indices: np.ndarray, st: EmaState, ema_decay: float = 0.99,
+               epsilon: float = 1e-5) -> EmaState:
+    """The ``self.training and use_ema`` block of the improved quantiser (index_improve/models/vq.py:146-187).
+
+    Scalars are Python doubles rounded to fp32 when they meet an fp32 tensor; ``index_add_`` on the CPU adds the
+    rows of a code in ascending item order (``np.add.at`` does the same); the convex update of the codebook is three
+    separate roundings (mul, mul, add), only for codes whose smoothed count exceeds ``epsilon``.
+    """
+    latent = latent.astype(F32, copy=False).reshape(-1, st.codebook.shape[1])
+    idx = np.asarray(indices).reshape(-1).astype(np.int64)
+    k, d = st.codebook.shape
+    decay32, alpha32 = F32(ema_decay), F32(1 - ema_decay)
+    counts = np.bincount(idx, minlength=k).astype(F32)                                   # vq.py:151-152
+    cs = _fma32(counts, alpha32, (st.cluster_size.astype(F32) * decay32).astype(F32))    # vq.py:155-157
+    dw = np.zeros((k, d), dtype=F32)
+    np.add.at(dw, idx, latent)                                                           # vq.py:163-167, item order
+    w = _fma32(dw, alpha32, (st.ema_w.astype(F32) * decay32).astype(F32))                # vq.py:169
+    normalized = (w / (cs[:, None] + F32(epsilon)).astype(F32)).astype(F32)              # vq.py:173
+    used = cs > F32(epsilon)                                                             # vq.py:176
+    update_rate = 1 - ema_decay
+    cb = st.codebook.astype(F32, copy=True)
+    cb[used] = ((cb[used] * F32(1 - update_rate)).astype(F32)
+                + (normalized[used] * F32(update_rate)).astype(F32)).astype(F32)         # vq.py:181-184
+    return EmaState(cb, cs, w, st.step_count + 1)
+
+
+def codebook_usage(cluster_size: np.ndarray, epsilon: float = 1e-5, reset_threshold: float = 1e-5):
+    """``get_codebook_usage`` (index_improve/models/vq.py:205-217): (utilization, used_codes, total_codes)."""
+    cs = cluster_size.astype(F32)
+    total = F32(cs.sum(dtype=F32) + F32(epsilon))
+    usage = (cs / total).astype(F32)
+    used = int((usage > F32(reset_threshold)).sum())
+    return used / cs.shape[0], used, int(cs.shape[0])
+
+
+def unused_codes(cluster_size: np.ndarray, epsilon: float = 1e-5, reset_threshold: float = 1e-5) -> np.ndarray:
+    """Indices ``_reset_unused_codes`` would consider dead (index_improve/models/vq.py:83-90); the replacement
+    vectors themselves are drawn from torch's RNG (randint / randperm / randn_like) and are not restated."""
+    cs = cluster_size.astype(F32)
+    usage = (cs / F32(cs.sum(dtype=F32) + F32(epsilon))).astype(F32)
+    return np.nonzero(usage < F32(reset_threshold))[0].astype(np.int64)
+
+
+def vq_forward_ema(x: np.ndarray, st: EmaState, use_sk: bool, sk_epsilon: float, sk_iters: int, beta: float,
+                   ema_decay: float = 0.99, epsilon: float = 1e-5, use_ema: bool = True, training: bool = True):
+    """Forward values of the improved quantiser for one step that does not cross ``reset_interval``
+    (index_improve/models/vq.py:115-203): the loss and x_q use the codebook BEFORE the EMA step."""
+    x_q, loss, idx = vq_forward(x, st.codebook, use_sk, sk_epsilon, sk_iters, beta)
+    if training and use_ema:
+        st = ema_update(x, idx, st, ema_decay, epsilon)
+    return x_q, loss, idx, st
+
+
+# --------------------------------------------------------------------------- #
+# f4: upstream embedding producer hand-off (masked mean pool of the PLM's last hidden state)
+# --------------------------------------------------------------------------- #
+def masked_mean_pool(hidden: np.ndarray, attention_mask: np.ndarray) -> np.ndarray:
+    """``(h * mask[..., None]).sum(1) / mask.sum(-1, keepdim=True)`` (data_process/amazon_text_emb.py:91-92), fp32;
+    rows are added in position order."""
+    h = hidden.astype(F32, copy=False)
+    m = np.asarray(attention_mask)
+    acc = np.zeros((h.shape[0], h.shape[2]), dtype=F32)
+    for t in range(h.shape[1]):
+        acc = (acc + (h[:, t, :] * m[:, t, None].astype(F32)).astype(F32)).astype(F32)
+    return (acc / m.sum(axis=-1, keepdims=True).astype(F32)).astype(F32)
+
+
+def item_embedding(field_hiddens: Sequence[np.ndarray], field_masks: Sequence[np.ndarray]) -> np.ndarray:
+    """Mean over the text fields of the per-field pools: ``torch.stack(field_embeddings, 0).mean(0)``
+    (data_process/amazon_text_emb.py:96)."""
+    pools = [masked_mean_pool(h, m) for h, m in zip(field_hiddens, field_masks)]
+    acc = pools[0]
+    for q in pools[1:]:
+        acc = (acc + q).astype(F32)
+    return (acc / F32(len(pools))).astype(F32)
+
+
+# --------------------------------------------------------------------------- #
 # a9/a10: residual quantiser and the model
 # --------------------------------------------------------------------------- #
 def rq_forward(z: np.ndarray, p: RqvaeParams, use_sk: bool):

@@ -97,3 +97,57 @@ def test_collision_bookkeeping():
     assert O.max_conflicts(codes) == 3
     assert abs(O.collision_rate(codes) - 0.5) < 1e-12
     assert json.loads(O.index_json(codes[:1])) == {"0": ["<a_1>", "<b_2>", "<c_3>", "<d_4>"]}
+
+
+# ------------------------------------------------------------------ f3: index_improve EMA quantiser
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_ema_quantiser_matches_reference(golden, case):
+    """Oracle vs the unmodified index_improve VectorQuantizer in training mode (oracle/make_golden_ema.py): indices,
+    loss, and BIT-identical codebook / _ema_cluster_size / _ema_w after every step; usage counts; dead-code set."""
+    g = golden("ema_kat")
+    n_e, e_dim, use_sk, _ = (int(v) for v in g[f"c{case}_cfg"])
+    eps = float(g[f"c{case}_sk_eps"])
+    st = O.EmaState(g[f"c{case}_codebook0"].copy(), np.zeros(n_e, np.float32), np.zeros((n_e, e_dim), np.float32))
+    resets = 0
+    for s in range(int(g[f"c{case}_steps"])):
+        x = g[f"c{case}_s{s}_x"]
+        _, loss, idx, st = O.vq_forward_ema(x, st, bool(use_sk), eps, 50, 0.25)
+        assert (idx == g[f"c{case}_s{s}_idx"]).all()
+        np.testing.assert_allclose(loss, g[f"c{case}_s{s}_loss"], rtol=1e-5)
+        if f"c{case}_s{s}_pre_reset_cs" in g:          # this step crossed reset_interval (RNG-driven; teacher-forced)
+            resets += 1
+            assert np.array_equal(st.cluster_size, g[f"c{case}_s{s}_pre_reset_cs"])
+            assert np.array_equal(st.codebook, g[f"c{case}_s{s}_pre_reset_codebook"])
+            dead = set(O.unused_codes(st.cluster_size).tolist())
+            after = g[f"c{case}_s{s}_codebook"]
+            changed = np.nonzero((after != st.codebook).any(axis=1))[0]
+            assert len(changed) == min(len(dead), x.shape[0]) and set(changed.tolist()) <= dead
+            assert (g[f"c{case}_s{s}_cs"][changed] == 0).all() and (g[f"c{case}_s{s}_w"][changed] == 0).all()
+            st = O.EmaState(after.copy(), g[f"c{case}_s{s}_cs"].copy(), g[f"c{case}_s{s}_w"].copy(), st.step_count)
+        else:
+            assert np.array_equal(st.codebook, g[f"c{case}_s{s}_codebook"])
+            assert np.array_equal(st.cluster_size, g[f"c{case}_s{s}_cs"])
+            assert np.array_equal(st.ema_w, g[f"c{case}_s{s}_w"])
+        util, used, total = O.codebook_usage(st.cluster_size)
+        assert [util, used, total] == g[f"c{case}_s{s}_usage"].tolist()
+    assert resets == (1 if case == 2 else 0)
+
+
+# ------------------------------------------------------------------ f4: embedding producer hand-off
+def _standin_hidden(g, j):
+    ids, mask = g[f"ids_{j}"], g[f"mask_{j}"]
+    h = g["E"][ids] + g["P"][: ids.shape[1]][None]
+    return (h + (1 - mask)[..., None] * np.float32(1e3)).astype(np.float32), mask
+
+
+def test_masked_mean_pool_matches_reference_producer(golden):
+    """Oracle vs the .npy the unmodified generate_item_embedding wrote (oracle/make_golden_pool.py).  Floating point:
+    torch's CPU sum over the sequence is a cascade, the oracle adds in position order - bar 1e-6 of the row scale
+    (measured 1.6e-7; bit-equal for sequences up to 16 positions)."""
+    g = golden("pool_kat")
+    nf = int(g["n_fields"])
+    for i in range(int(g["n_items"])):
+        hs, ms = zip(*[_standin_hidden(g, nf * i + f) for f in range(nf)])
+        assert any((m == 0).any() for m in ms) or i > 0
+        e = O.item_embedding(hs, ms)[0]
+        assert np.abs(e - g["emb"][i]).max() <= 1e-6 * np.abs(g["emb"][i]).max()
