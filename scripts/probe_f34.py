@@ -1,13 +1,15 @@
 """Timing of the 8(f) kernels on one B200 (CUDA events, warm): masked mean pool (HBM-bound: bytes of hidden state read /
 time vs the measured copy peak) and the EMA codebook step.  Prints one JSON line per case."""
 import json
+import os
+import sys
 
-import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
 
-from lcrec_b200 import ops
+from lcrec_b200 import ops  # noqa: E402
 
 DEV = torch.device("cuda:0")
-PEAK = json.load(open("MEASURED_PEAKS.json")) if __import__("os").path.exists("MEASURED_PEAKS.json") else {}
 
 
 def timed(fn, reps=20):
