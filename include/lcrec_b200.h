@@ -248,6 +248,22 @@ int lcrec_indexer_resolve(lcrec_indexer_t* ix, int64_t* codes, const float* resi
 int lcrec_indexer_set_segments(int on);
 int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
 float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */
+/* ---- f1: k-means codebook initialisation (index/models/layers.py:69-82 -> sklearn.cluster.KMeans(n_clusters,
+ * max_iter).fit; scikit-learn `_kmeans_single_lloyd`) ------------------------------------------------------------------
+ * The k-means++ seeding stays with scikit-learn on the host (it consumes numpy's global RNG like the reference); the
+ * Lloyd iterations run here with sklearn's structure (centred data, lowest-index nearest centre, per-cluster sums in item
+ * order times the reciprocal count, empty clusters take the farthest points, stop on unchanged labels or on a total
+ * squared centre shift <= tol, final E-step if the stop was not strict).
+ * lcrec_kmeans_center: xc = x - column means (n, e_dim); mean (e_dim) device; *mean_variance_host = mean of the column
+ * variances (sklearn's tol is 1e-4 times that).  lcrec_kmeans_lloyd: centers (n_codes, e_dim) holds the seeds on entry (in
+ * the centred frame) and the result on exit, `add_mean` (nullable) is added at the end; labels_out (nullable, n int64),
+ * *inertia_host, *n_iter_host as KMeans.inertia_ / n_iter_.  Synchronises the stream once per iteration (24 bytes D2H). */
+int64_t lcrec_kmeans_workspace_bytes(int64_t n, int e_dim, int n_codes);
+int lcrec_kmeans_center(const float* x, int64_t n, int e_dim, float* xc, float* mean, double* mean_variance_host,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int lcrec_kmeans_lloyd(const float* xc, int64_t n, int e_dim, float* centers, int n_codes, int max_iter, double tol,
+                       const float* add_mean, int64_t* labels_out, double* inertia_host, int* n_iter_host,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 /* ---- f3: EMA codebook variant (index_improve/models/vq.py) ----------------------------------
  * lcrec_ema_update: the `self.training and use_ema` block of the improved VectorQuantizer.forward
  * (index_improve/models/vq.py:146-187) in place on the module's buffers: per-code counts of `indices` (n,) int64,

@@ -79,6 +79,10 @@ SIGNATURES = {
     "lcrec_codebook_usage": (C.c_int, [vp, C.c_int, f64, f64, vp, vp, vp]),
     "lcrec_masked_mean_pool_workspace_bytes": (i64, [i64, i64, C.c_int]),
     "lcrec_masked_mean_pool": (C.c_int, [vp, C.c_int, vp, i64, i64, C.c_int, vp, i64, C.c_int, f64, vp, i64, vp]),
+    "lcrec_kmeans_workspace_bytes": (i64, [i64, C.c_int, C.c_int]),
+    "lcrec_kmeans_center": (C.c_int, [vp, i64, C.c_int, vp, vp, C.POINTER(f64), vp, i64, vp]),
+    "lcrec_kmeans_lloyd": (C.c_int, [vp, i64, C.c_int, vp, C.c_int, C.c_int, f64, vp, vp, C.POINTER(f64), C.POINTER(C.c_int),
+                                     vp, i64, vp]),
     "lcrec_indexer_codes": (vp, [vp]),
     "lcrec_indexer_resid": (vp, [vp]),
 }

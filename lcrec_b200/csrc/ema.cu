@@ -1,73 +1,26 @@
 // EMA codebook update, usage statistics (reference index_improve/models/vq.py:146-187, 205-217).
 //
-// One CTA owns one code k: it walks the assignment vector in item order, compacts the items assigned to k into a
-// shared-memory list that keeps their order (warp ballots + prefix), and lets thread d add latent[item][d] to its
-// running sum in exactly that order - the summation order of torch's CPU index_add_ (vq.py:166-167), so the sums are
-// bit-identical to the reference and independent of the grid (deterministic, no floating-point atomics).  The same CTA
+// One CTA owns one code k: ordered_code_sum (segsum.cuh) adds the rows assigned to k in ascending item order - the
+// summation order of torch's CPU index_add_ (vq.py:166-167), so the sums are bit-identical to the reference and
+// independent of the grid (deterministic, no floating-point atomics).  The same CTA
 // then applies the smoothing and the convex codebook update with the reference's roundings: `x.mul_(decay)` is one
 // rounding, `.add_(t, alpha=a)` is a fused multiply-add, `c * (1 - r) + n * r` is three roundings.
 #include "common.cuh"
+#include "segsum.cuh"
 
 namespace lcrec {
 
-constexpr int kEmaThreads = 128;
-constexpr int kEmaList = 2048;     // members buffered between flushes
+constexpr int kEmaThreads = kSegThreads;
 
 __global__ void __launch_bounds__(kEmaThreads)
 ema_update_kernel(const float* __restrict__ latent, const int64_t* __restrict__ indices, int64_t n, int e_dim,
                   float decay, float alpha, float eps, float keep, float rate,
                   float* __restrict__ cluster_size, float* __restrict__ ema_w, float* __restrict__ codebook) {
   extern __shared__ float acc[];                 // e_dim running sums
-  __shared__ int list[kEmaList];
-  __shared__ int warp_total[kEmaThreads / 32];
+  __shared__ SegSumSmem sm;
   const int k = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int d = tid; d < e_dim; d += kEmaThreads) acc[d] = 0.f;
-  int filled = 0;
-  int64_t count = 0;
-  __syncthreads();
-
-  auto flush = [&]() {
-    for (int d = tid; d < e_dim; d += kEmaThreads) {
-      float a = acc[d];
-      int j = 0;
-      for (; j + 4 <= filled; j += 4) {          // loads issued together, additions in list order
-        const float v0 = latent[(int64_t)list[j] * e_dim + d];
-        const float v1 = latent[(int64_t)list[j + 1] * e_dim + d];
-        const float v2 = latent[(int64_t)list[j + 2] * e_dim + d];
-        const float v3 = latent[(int64_t)list[j + 3] * e_dim + d];
-        a = __fadd_rn(a, v0); a = __fadd_rn(a, v1); a = __fadd_rn(a, v2); a = __fadd_rn(a, v3);
-      }
-      for (; j < filled; ++j) a = __fadd_rn(a, latent[(int64_t)list[j] * e_dim + d]);
-      acc[d] = a;
-    }
-  };
-
-  for (int64_t base = 0; base < n; base += kEmaThreads) {
-    const int64_t i = base + tid;
-    const bool hit = i < n && indices[i] == (int64_t)k;
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) warp_total[warp] = __popc(m);
-    __syncthreads();
-    int before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kEmaThreads / 32; ++w) {
-      const int t = warp_total[w];
-      before += w < warp ? t : 0;
-      total += t;
-    }
-    if (hit) list[filled + before + __popc(m & ((1u << lane) - 1u))] = (int)i;   // n < 2^31 is checked on the host
-    filled += total;
-    count += total;
-    __syncthreads();
-    if (filled > kEmaList - kEmaThreads) {
-      flush();
-      filled = 0;
-      __syncthreads();
-    }
-  }
-  flush();
-  __syncthreads();
+  const int tid = threadIdx.x;
+  const int64_t count = ordered_code_sum(latent, indices, n, e_dim, k, acc, sm);
 
   // smoothing + codebook step (vq.py:155-184)
   const float cs = fmaf((float)count, alpha, __fmul_rn(cluster_size[k], decay));

@@ -15,6 +15,7 @@ CUDA only - a CPU tensor raises (no fallback).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -211,14 +212,31 @@ class MLPLayers(nn.Module):
         return x
 
 
+# "sklearn": the reference's own call, bit-reproducible against it.  "device": k-means++ seeding by scikit-learn on the host
+# (same draws from numpy's global RNG as KMeans.fit), Lloyd iterations in liblcrec_b200.so (lcrec_kmeans_lloyd).
+KMEANS_BACKEND = os.environ.get("LCREC_KMEANS", "sklearn")
+
+
 def kmeans(samples, num_clusters, num_iters=10):
-    """Codebook initialisation (reference layers.py:69-82).  Delegated to scikit-learn exactly as
-    the reference does (k-means++ seeding from numpy's global RNG) so that initial codebooks are
-    reproducible against it; a device k-means is listed under 'next' in DESIGN.md."""
-    from sklearn.cluster import KMeans
-    x = samples.detach().cpu().numpy()
-    fit = KMeans(n_clusters=num_clusters, max_iter=num_iters).fit(x)
-    return torch.from_numpy(fit.cluster_centers_).to(samples.device)
+    """Codebook initialisation (reference layers.py:69-82: sklearn ``KMeans(n_clusters, max_iter).fit`` on the CPU copy).
+
+    Backend "sklearn" delegates exactly as the reference does.  Backend "device" keeps only the k-means++ seeding on the
+    host - ``sklearn.cluster.kmeans_plusplus`` on the centred batch consumes numpy's global RNG exactly like ``fit`` (tested)
+    - and runs sklearn's Lloyd loop (centring, tol = 1e-4 x mean column variance, strict / tol stop, empty-cluster
+    relocation, final E-step) on the device; centres agree with sklearn's to fp32 rounding whenever the label sequences
+    coincide (tests/test_gpu_zz_kmeans.py)."""
+    if KMEANS_BACKEND == "sklearn":
+        from sklearn.cluster import KMeans
+        x = samples.detach().cpu().numpy()
+        fit = KMeans(n_clusters=num_clusters, max_iter=num_iters).fit(x)
+        return torch.from_numpy(fit.cluster_centers_).to(samples.device)
+    if KMEANS_BACKEND != "device":
+        raise ValueError(f"unknown k-means backend {KMEANS_BACKEND!r}")
+    from sklearn.cluster import kmeans_plusplus
+    xc, mean, mean_var = ops.kmeans_center(samples.detach())
+    seeds, _ = kmeans_plusplus(xc.cpu().numpy(), num_clusters)
+    fit = ops.kmeans_lloyd(xc, torch.from_numpy(seeds).to(xc.device), num_iters, 1e-4 * mean_var, add_mean=mean)
+    return fit["centers"]
 
 
 @torch.no_grad()

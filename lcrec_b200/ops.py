@@ -253,6 +253,40 @@ def vq_distances(r: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# --------------------------------------------------------------------------- k-means initialisation
+def kmeans_center(x: torch.Tensor):
+    """(x - column means, means, mean of the column variances): the frame sklearn's KMeans.fit works in."""
+    _need_cuda(x)
+    lib = _lib.load()
+    x2 = _f32c(x.reshape(-1, x.shape[-1]))
+    n, d = x2.shape
+    xc = torch.empty_like(x2)
+    mean = torch.empty(d, dtype=torch.float32, device=x2.device)
+    var = C.c_double(0.0)
+    ws = _ws(lib.lcrec_kmeans_workspace_bytes(n, d, 1), x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.lcrec_kmeans_center(_p(x2), n, d, _p(xc), _p(mean), C.byref(var), _p(ws), ws.numel(), _stream(x2)))
+    return xc, mean, float(var.value)
+
+
+def kmeans_lloyd(xc: torch.Tensor, seeds: torch.Tensor, max_iter: int, tol: float, add_mean: Optional[torch.Tensor] = None):
+    """Lloyd iterations from ``seeds`` on centred data -> dict(centers, labels, inertia, n_iter) (sklearn semantics)."""
+    _need_cuda(xc, seeds, add_mean)
+    lib = _lib.load()
+    x2 = _f32c(xc)
+    n, d = x2.shape
+    centers = _f32c(seeds).clone()
+    k = centers.shape[0]
+    labels = torch.empty(n, dtype=torch.int64, device=x2.device)
+    inertia, n_iter = C.c_double(0.0), C.c_int(0)
+    ws = _ws(lib.lcrec_kmeans_workspace_bytes(n, d, k), x2.device)
+    am = None if add_mean is None else _f32c(add_mean)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.lcrec_kmeans_lloyd(_p(x2), n, d, _p(centers), k, int(max_iter), float(tol), _p(am), _p(labels),
+                                          C.byref(inertia), C.byref(n_iter), _p(ws), ws.numel(), _stream(x2)))
+    return {"centers": centers, "labels": labels, "inertia": float(inertia.value), "n_iter": int(n_iter.value)}
+
+
 # --------------------------------------------------------------------------- EMA codebook variant
 def _inplace_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != torch.float32 or not t.is_contiguous():
