@@ -114,6 +114,21 @@ int lcrec_rq_quantize(const float* z, int64_t n, int e_dim, int n_levels, const 
  * and smaller batches: SIMT kernels), 2 = whenever the shape allows it (cross-checks). */
 int lcrec_rq_set_tc_mode(int mode);
 
+/* ---- a9/a11: training-side residual quantiser for GIVEN codes (rq.py:39-56 over vq.py:87-99) -------------------------
+ * forward: xq (n, D) = sum of x_res over the levels, diffs (L, n, D) = q_l - r_l per level, codes_t (L, n) = transposed
+ * codes, sq_err (L) fp64 = sum |q_l - r_l|^2 (loss_l = (1 + beta) * sq_err_l / (n D)); values identical to the per-level
+ * torch ops of the reference.  backward: analytic gradients of (x_q, mean of the level losses) - the straight-through
+ * estimator leaves d x_q / d z = I and only level 0's commitment term reaches z:
+ *   g_z = g_xq - g_loss / L * beta0 * 2 / (n D) * diffs[0];  g_codebooks[l][k] = g_loss / L * 2 / (n D) * sum of diffs[l]
+ * over the rows with code k, added in item order (deterministic).  g_xq (nullable = 0) (n, D); g_loss: ONE fp32 on the
+ * device (nullable = 0); g_z / g_codebooks nullable. */
+int lcrec_rq_train_forward(const float* z, const int64_t* codes, int64_t n, int e_dim, int n_levels,
+                           const float* const* codebooks, float* xq, float* diffs, int64_t* codes_t, double* sq_err,
+                           void* stream);
+int lcrec_rq_train_backward(const float* diffs, const int64_t* codes_t, int64_t n, int e_dim, int n_levels,
+                            const int32_t* n_codes, const float* g_xq, const float* g_loss, double beta0, float* g_z,
+                            float* const* g_codebooks, void* stream);
+
 /* ---- a4: distances only (index/models/vq.py:71-73), (n, K) fp32 ------------------------ */
 int lcrec_vq_distances(const float* r, int64_t n, int e_dim, const float* codebook, int n_codes,
                        float* d, void* stream);

@@ -83,6 +83,8 @@ SIGNATURES = {
     "lcrec_kmeans_center": (C.c_int, [vp, i64, C.c_int, vp, vp, C.POINTER(f64), vp, i64, vp]),
     "lcrec_kmeans_lloyd": (C.c_int, [vp, i64, C.c_int, vp, C.c_int, C.c_int, f64, vp, vp, C.POINTER(f64), C.POINTER(C.c_int),
                                      vp, i64, vp]),
+    "lcrec_rq_train_forward": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, pp, vp, vp, vp, vp, vp]),
+    "lcrec_rq_train_backward": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, C.POINTER(i32), vp, vp, f64, vp, pp, vp]),
     "lcrec_indexer_codes": (vp, [vp]),
     "lcrec_indexer_resid": (vp, [vp]),
 }

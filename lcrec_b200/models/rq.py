@@ -14,6 +14,51 @@ from .. import ops
 from .vq import VectorQuantizer
 
 
+# Training forward through ONE autograd node (lcrec_rq_train_forward / _backward) instead of the per-level torch glue;
+# False restores the per-level modules (cross-checks).
+FUSED_TRAIN = True
+
+
+class _RQTrainFn(torch.autograd.Function):
+    """(x_q, mean level loss, indices) of rq.py:39-56 with the analytic backward of the straight-through estimator:
+    d x_q / d z = I, only level 0's commitment term reaches z, codebooks receive the codebook-loss term (summed in item
+    order, deterministic).  Values and gradients equal the per-level autograd path to fp32 rounding (tested)."""
+
+    @staticmethod
+    def forward(ctx, z, rq, use_sk, *codebooks):
+        d = rq.e_dim
+        lat = z.detach().reshape(-1, d).float().contiguous()
+        n = lat.shape[0]
+        codes = rq.assign_codes(lat, use_sk)
+        r = ops.rq_train_forward(lat, codes, [c.detach() for c in codebooks])
+        mse = (r["sq_err"] / max(n * d, 1)).to(torch.float32)
+        betas = [float(l.beta) for l in rq.vq_layers]
+        if any(b != betas[0] for b in betas):                        # per-level betas: a (cached) device vector
+            key = (tuple(betas), lat.device)
+            if getattr(rq, "_beta_vec_key", None) != key:
+                rq._beta_vec, rq._beta_vec_key = torch.tensor(betas, dtype=torch.float32, device=lat.device), key
+            mean_loss = (mse + rq._beta_vec * mse).mean()
+        else:
+            mean_loss = (mse + betas[0] * mse).mean()                # codebook_loss + beta * commitment_loss, stack().mean()
+        ctx.save_for_backward(r["diffs"], r["codes_t"])
+        ctx.n_codes = [int(c.shape[0]) for c in codebooks]
+        ctx.beta0 = float(rq.vq_layers[0].beta)
+        ctx.z_shape = z.shape
+        indices = codes.view(*z.shape[:-1], len(codebooks))
+        ctx.mark_non_differentiable(indices)
+        return r["xq"].view(z.shape), mean_loss, indices
+
+    @staticmethod
+    def backward(ctx, g_xq, g_loss, _g_idx):
+        diffs, codes_t = ctx.saved_tensors
+        need_z = ctx.needs_input_grad[0]
+        need_cb = any(ctx.needs_input_grad[3:])
+        gz, gcbs = ops.rq_train_backward(diffs, codes_t, ctx.n_codes, g_xq, g_loss, ctx.beta0, want_gz=need_z,
+                                         want_gcb=need_cb)
+        gz = gz.view(ctx.z_shape) if need_z else None
+        return (gz, None, None) + (tuple(gcbs) if need_cb else (None,) * len(ctx.n_codes))
+
+
 class ResidualVectorQuantizer(nn.Module):
     def __init__(self, n_e_list, e_dim, sk_epsilons, beta=0.25, kmeans_init=False, kmeans_iters=100, sk_iters=100):
         super().__init__()
@@ -32,6 +77,35 @@ class ResidualVectorQuantizer(nn.Module):
 
     def get_codebook(self):
         return torch.stack([q.get_codebook() for q in self.vq_layers])
+
+    # ------------------------------------------------------------------ index selection for all levels, no autograd
+    @torch.no_grad()
+    def assign_codes(self, lat, use_sk=True):
+        """(n, L) int64 codes of rq.py:45-52: runs of argmin levels in the fused kernel, Sinkhorn levels through
+        VectorQuantizer.assign on the residual entering them."""
+        layers = list(self.vq_layers)
+        resid = lat
+        codes = []
+        i = 0
+        while i < len(layers):
+            j = i
+            while j < len(layers) and not (use_sk and layers[j].sk_epsilon > 0):
+                j += 1
+            if j > i:
+                last = j == len(layers)
+                r = ops.rq_quantize(resid, [l.embedding.weight for l in layers[i:j]], resid_level=-1 if last else j - i)
+                codes.append(r["codes"])
+                resid = r["resid"]
+                i = j
+            if i < len(layers):
+                l = layers[i]
+                idx = l.assign(resid, use_sk=True)
+                codes.append(idx[:, None])
+                i += 1
+                if i < len(layers):
+                    q = l.embedding.weight.detach()[idx]
+                    resid = resid - (resid + (q - resid))
+        return torch.cat(codes, dim=1).contiguous()
 
     # ------------------------------------------------------------------ fused, no autograd
     @torch.no_grad()
@@ -78,6 +152,8 @@ class ResidualVectorQuantizer(nn.Module):
         pending_init = self.training and any(not q.initted for q in self.vq_layers)
         if not needs_graph and not pending_init:
             return self.quantize_fused(x, use_sk)
+        if FUSED_TRAIN and not pending_init and type(self).forward is ResidualVectorQuantizer.forward:
+            return _RQTrainFn.apply(x, self, use_sk, *[q.embedding.weight for q in self.vq_layers])
         all_losses, all_indices = [], []
         x_q = 0
         residual = x

@@ -65,13 +65,10 @@ class VectorQuantizer(nn.Module):
         if self.dist_sinkhorn is not None:
             dc = self.dist_sinkhorn.center(d)                          # max / min over the global batch
             _, idx, flags = self.dist_sinkhorn(dc, self.sk_epsilon, self.sk_iters)
-            if int(flags.item()) & 8:
-                raise RuntimeError("distributed Sinkhorn: a peer rank did not arrive")
         else:
             dc = ops.center_distances(d)                              # fp64, raises AssertionError like vq.py:59
             _, idx, flags = ops.sinkhorn_dense(dc, self.sk_epsilon, self.sk_iters, want_argmax=True)
-        if int(flags.item()) & 1:
-            print("Sinkhorn Algorithm returns nan/inf values.")        # vq.py:81-82
+        ops.check_later("sinkhorn", flags)                            # peer-arrival error; NaN/Inf print of vq.py:81-82
         return idx
 
     def get_code(self, x, use_sk=True):

@@ -67,6 +67,55 @@ def profile_collect() -> dict:
     return {t: (ms[t], int(calls[t])) for t in range(32) if calls[t]}
 
 
+# --------------------------------------------------------------------------- host-visible status words
+# The reference reads two device flags on the host inside VectorQuantizer.forward (the Python `assert` of vq.py:59 and the
+# NaN/Inf print of vq.py:81-82).  By default they are read where the reference reads them.  A training loop can wrap its
+# step in `defer_checks()`: the flags are queued and evaluated by `flush_checks()` at the end of the step (where the
+# reference loop synchronises anyway for `loss.item()`), so the forward pass enqueues without draining the GPU.
+_DEFER = False
+_PENDING: List[Tuple[str, torch.Tensor]] = []
+
+
+def _evaluate_check(kind: str, word: torch.Tensor) -> None:
+    v = int(word.item())
+    if kind == "amplitude" and v != 0:
+        raise AssertionError("amplitude > 0")
+    if kind == "sinkhorn":
+        if v & 8:
+            raise RuntimeError("distributed Sinkhorn: a peer rank did not arrive")
+        if v & 1:
+            print("Sinkhorn Algorithm returns nan/inf values.")
+
+
+def check_later(kind: str, word: torch.Tensor) -> None:
+    if _DEFER:
+        _PENDING.append((kind, word))
+    else:
+        _evaluate_check(kind, word)
+
+
+def flush_checks() -> None:
+    pending, _PENDING[:] = list(_PENDING), []
+    for kind, word in pending:
+        _evaluate_check(kind, word)
+
+
+class defer_checks:
+    def __enter__(self):
+        global _DEFER
+        self._old, _DEFER = _DEFER, True
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFER
+        _DEFER = self._old
+        if exc[0] is None and not _DEFER:
+            flush_checks()
+        elif exc[0] is not None:
+            _PENDING.clear()
+        return False
+
+
 # --------------------------------------------------------------------------- MLP
 class MlpHandle:
     """Prepared (hi/lo-split) weights of one MLPLayers stack."""
@@ -241,6 +290,45 @@ def rq_quantize(z: torch.Tensor, codebooks: Sequence[torch.Tensor], n_levels_run
     return {"codes": codes, "xq": xq, "resid": resid, "sq_err": err}
 
 
+def rq_train_forward(z: torch.Tensor, codes: torch.Tensor, codebooks: Sequence[torch.Tensor]):
+    """Forward values of the residual quantiser for given codes (rq.py:39-56): dict(xq (n, D), diffs (L, n, D),
+    codes_t (L, n), sq_err (L) fp64)."""
+    _need_cuda(z, codes, *codebooks)
+    lib = _lib.load()
+    cbs = [_f32c(c) for c in codebooks]
+    L, d = len(cbs), int(cbs[0].shape[1])
+    z2 = _f32c(z.reshape(-1, d))
+    n = z2.shape[0]
+    c2 = codes.detach().reshape(n, L).to(torch.int64).contiguous()
+    dev = z2.device
+    xq = torch.empty((n, d), dtype=torch.float32, device=dev)
+    diffs = torch.empty((L, n, d), dtype=torch.float32, device=dev)
+    codes_t = torch.empty((L, n), dtype=torch.int64, device=dev)
+    err = torch.empty((L,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.lcrec_rq_train_forward(_p(z2), _p(c2), n, d, L, _lib.ptr_array([c.data_ptr() for c in cbs]), _p(xq),
+                                              _p(diffs), _p(codes_t), _p(err), _stream(z2)))
+    return {"xq": xq, "diffs": diffs, "codes_t": codes_t, "sq_err": err}
+
+
+def rq_train_backward(diffs: torch.Tensor, codes_t: torch.Tensor, n_codes: Sequence[int], g_xq: Optional[torch.Tensor],
+                      g_loss: Optional[torch.Tensor], beta0: float, want_gz: bool = True, want_gcb: bool = True):
+    """Analytic backward of (x_q, mean level loss) w.r.t. (z, codebooks); see include/lcrec_b200.h."""
+    _need_cuda(diffs, codes_t, g_xq, g_loss)
+    lib = _lib.load()
+    L, n, d = diffs.shape
+    dev = diffs.device
+    gx = None if g_xq is None else _f32c(g_xq.reshape(n, d))
+    gl = None if g_loss is None else _f32c(g_loss.reshape(1))
+    gz = torch.empty((n, d), dtype=torch.float32, device=dev) if want_gz else None
+    gcbs = [torch.empty((int(k), d), dtype=torch.float32, device=dev) for k in n_codes] if want_gcb else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.lcrec_rq_train_backward(
+            _p(diffs), _p(codes_t), n, d, L, _lib.i32_array(list(n_codes)), _p(gx), _p(gl), float(beta0), _p(gz),
+            _lib.ptr_array([g.data_ptr() for g in gcbs]) if want_gcb else None, _stream(diffs)))
+    return gz, gcbs
+
+
 def vq_distances(r: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
     """(n, K) fp32 distances of vq.py:71-73."""
     _need_cuda(r, codebook)
@@ -367,8 +455,7 @@ def center_distances(d: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(d2.device):
         _lib.check(lib.lcrec_center_distances(_p(d2), d2.shape[0], d2.shape[1], _p(out), _p(status), _p(ws),
                                               ws.numel(), _stream(d2)))
-    if int(status.item()) != 0:
-        raise AssertionError("amplitude > 0")      # vq.py:59
+    check_later("amplitude", status)                # vq.py:59 (a host read; deferred to the end of the step under defer_checks)
     return out
 
 

@@ -101,16 +101,19 @@ class Trainer(object):
         bar = tqdm(train_data, total=len(train_data), ncols=100, desc=set_color(f"Train {epoch_idx}", "pink"))
         for data in bar:
             data = data.to(self.device)
-            self.optimizer.zero_grad()
-            out, rq_loss, _ = self._model_forward(data)
-            loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=data)
-            self._check_nan(loss)
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
-            self.optimizer.step()
-            self.scheduler.step()
-            total_loss += loss.item()
-            total_recon_loss += loss_recon.item()
+            # the two status words the reference reads on the host inside the forward pass (vq.py:59, :81-82) are read at
+            # the end of the step, where `loss.item()` synchronises anyway: the step is enqueued without draining the GPU
+            with ops.defer_checks():
+                self.optimizer.zero_grad()
+                out, rq_loss, _ = self._model_forward(data)
+                loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=data)
+                self._check_nan(loss)
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+                self.optimizer.step()
+                self.scheduler.step()
+                total_loss += loss.item()
+                total_recon_loss += loss_recon.item()
         return total_loss, total_recon_loss
 
     @torch.no_grad()
