@@ -30,7 +30,7 @@ def _run(rq, z0, use_sk, fused, w_xq):
 
 
 @pytest.mark.parametrize("n,d,ks,eps", [(1024, 32, [256] * 4, [0.0, 0.0, 0.0, 0.003]), (300, 16, [32, 32, 32], [0.0, 0.0, 0.0]),
-                                        (257, 100, [50, 20], [0.0, 0.003]), (64, 8, [16, 16, 16], [0.0, 0.003, 0.0]),
+                                        (257, 48, [100, 50], [0.0, 0.003]), (64, 16, [32, 32, 32], [0.0, 0.003, 0.0]),
                                         (1, 32, [256], [0.0])])
 def test_fused_rq_training_equals_per_level_autograd(n, d, ks, eps):
     torch.manual_seed(n + d)
