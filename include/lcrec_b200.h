@@ -129,6 +129,20 @@ int lcrec_rq_train_backward(const float* diffs, const int64_t* codes_t, int64_t 
                             const int32_t* n_codes, const float* g_xq, const float* g_loss, double beta0, float* g_z,
                             float* const* g_codebooks, void* stream);
 
+/* ---- a11: clip_grad_norm_(parameters, max_norm) + optimizer.step() for Adam / AdamW (index/trainer.py:49-81, :117-119) -
+ * All tensors in two launches.  Pass 1: sum of squares of every gradient (per-CTA partials, fixed order).  Pass 2: every CTA
+ * derives coef = min(1, max_norm / (||g|| + 1e-6)) from the partials, then per element (torch.optim semantics, fp32):
+ * g *= coef;  AdamW (decoupled = 1): p *= 1 - lr wd;  Adam (0): g += wd p;  m += (g - m)(1 - beta1);
+ * v = v beta2 + (1 - beta2) g^2;  p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps).
+ * params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors device pointers (fp32, contiguous), numel: host array;
+ * step >= 1 is the value AFTER this call's increment; max_norm <= 0 skips clipping; write_clipped_grads stores the clipped
+ * gradients back (what clip_grad_norm_ leaves in .grad); total_norm_out (nullable, 1 fp32 on the device) = ||g||. */
+int64_t lcrec_adam_workspace_bytes(int n_tensors, const int64_t* numel);
+int lcrec_adam_clip_step(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                         float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                         double weight_decay, int decoupled, int64_t step, double max_norm, int write_clipped_grads,
+                         float* total_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- a4: distances only (index/models/vq.py:71-73), (n, K) fp32 ------------------------ */
 int lcrec_vq_distances(const float* r, int64_t n, int e_dim, const float* codebook, int n_codes,
                        float* d, void* stream);

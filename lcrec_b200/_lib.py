@@ -85,6 +85,9 @@ SIGNATURES = {
                                      vp, i64, vp]),
     "lcrec_rq_train_forward": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, pp, vp, vp, vp, vp, vp]),
     "lcrec_rq_train_backward": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, C.POINTER(i32), vp, vp, f64, vp, pp, vp]),
+    "lcrec_adam_workspace_bytes": (i64, [C.c_int, C.POINTER(i64)]),
+    "lcrec_adam_clip_step": (C.c_int, [C.c_int, pp, pp, pp, pp, C.POINTER(i64), f64, f64, f64, f64, f64, C.c_int, i64, f64,
+                                       C.c_int, vp, vp, i64, vp]),
     "lcrec_indexer_codes": (vp, [vp]),
     "lcrec_indexer_resid": (vp, [vp]),
 }

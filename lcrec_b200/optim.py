@@ -1,0 +1,86 @@
+"""Adam / AdamW with fused gradient clipping on the device: ``clip_grad_norm_(params, max_norm)`` + ``optimizer.step()`` of
+reference ``index/trainer.py:117-119`` (optimisers built at :49-81) as two launches over all parameters
+(``lcrec_adam_clip_step``).  A ``torch.optim.Optimizer`` subclass with the state layout of ``torch.optim.AdamW``
+(``step`` / ``exp_avg`` / ``exp_avg_sq`` per parameter), so LR schedulers, ``state_dict()`` / ``load_state_dict()`` and the
+checkpoints of the reference Trainer (:154-172) work unchanged in both directions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled_weight_decay=decoupled, amsgrad=False,
+                        maximize=False, foreach=None, capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def clip_and_step(self, max_norm: float = 0.0, want_norm: bool = False):
+        """Gradient clipping to ``max_norm`` (<= 0: none) over ALL parameter groups (like ``clip_grad_norm_`` on
+        ``model.parameters()``) followed by the update.  Returns the total gradient norm (a device tensor) if asked."""
+        lib = _lib.load()
+        groups = []
+        all_grads = []
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            for p in ps:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
+                    raise RuntimeError("FusedAdam: contiguous fp32 CUDA parameters with dense gradients only "
+                                       "(lcrec_b200 has no CPU fallback)")
+                if not p.grad.is_contiguous():
+                    p.grad = p.grad.contiguous()
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            groups.append((group, ps))
+            all_grads += [p.grad for p in ps]
+        if not all_grads:
+            return None
+        dev = all_grads[0].device
+        norm_out = torch.zeros(1, dtype=torch.float32, device=dev) if (want_norm and max_norm > 0) else None
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            if max_norm > 0 and len(groups) > 1:
+                # one norm over every group: clip first (pass 1 + scaling through a zero-lr call is not needed: groups
+                # share the norm only if they are updated together, so merge groups with equal hyper-parameters)
+                raise RuntimeError("FusedAdam.clip_and_step: one parameter group expected when clipping")
+            for group, ps in groups:
+                if not ps:
+                    continue
+                steps = set()
+                for p in ps:
+                    st = self.state[p]
+                    st["step"] += 1                              # a CPU scalar tensor, as torch.optim keeps it
+                    steps.add(int(st["step"]))
+                if len(steps) != 1:
+                    raise RuntimeError("FusedAdam: parameters of one group must share the step count")
+                n = len(ps)
+                numel = (C.c_int64 * n)(*[p.numel() for p in ps])
+                ws_bytes = int(lib.lcrec_adam_workspace_bytes(n, numel))
+                if getattr(self, "_ws", None) is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+                    self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                b1, b2 = group["betas"]
+                _lib.check(lib.lcrec_adam_clip_step(
+                    n, _lib.ptr_array([p.data_ptr() for p in ps]), _lib.ptr_array([p.grad.data_ptr() for p in ps]),
+                    _lib.ptr_array([self.state[p]["exp_avg"].data_ptr() for p in ps]),
+                    _lib.ptr_array([self.state[p]["exp_avg_sq"].data_ptr() for p in ps]), numel, float(group["lr"]),
+                    float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(bool(group.get("decoupled_weight_decay", True))),
+                    steps.pop(), float(max_norm), 1, C.c_void_p(0 if norm_out is None else norm_out.data_ptr()),
+                    C.c_void_p(self._ws.data_ptr()), self._ws.numel(), stream))
+        return norm_out
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.clip_and_step(0.0)
+        return loss

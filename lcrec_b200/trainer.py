@@ -19,7 +19,12 @@ from torch.optim.lr_scheduler import LambdaLR
 from tqdm import tqdm
 
 from . import ops
+from .optim import FusedAdam
 from .utils import delete_file, ensure_dir, get_local_time, set_color
+
+
+# Adam / AdamW through lcrec_adam_clip_step (LCREC_FUSED_OPTIM=0: torch.optim + clip_grad_norm_)
+FUSED_OPTIM = os.environ.get("LCREC_FUSED_OPTIM", "1") != "0"
 
 
 def _linear_warmup_decay(optimizer, warmup, total):
@@ -71,6 +76,9 @@ class Trainer(object):
         kw = dict(lr=self.lr, weight_decay=self.weight_decay)
         table = {"adam": optim.Adam, "sgd": optim.SGD, "adagrad": optim.Adagrad, "rmsprop": optim.RMSprop,
                  "adamw": optim.AdamW}
+        if name in ("adam", "adamw") and FUSED_OPTIM and self.device.type == "cuda":
+            # same update rule and state layout as torch.optim.Adam / AdamW; clipping + step in two launches
+            return FusedAdam(params, decoupled=(name == "adamw"), **kw)
         if name in table:
             opt = table[name](params, **kw)
             if name == "adagrad":
@@ -109,8 +117,11 @@ class Trainer(object):
                 loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=data)
                 self._check_nan(loss)
                 loss.backward()
-                torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
-                self.optimizer.step()
+                if isinstance(self.optimizer, FusedAdam):
+                    self.optimizer.clip_and_step(1.0)                      # trainer.py:117-118 in one native call
+                else:
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+                    self.optimizer.step()
                 self.scheduler.step()
                 total_loss += loss.item()
                 total_recon_loss += loss_recon.item()

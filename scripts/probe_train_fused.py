@@ -11,10 +11,12 @@ dims = [2048, 1024, 512, 256, 128, 64]
 B, steps = 1024, 40
 x = torch.randn(B * 4, 4096, device=dev)
 out = {}
-for name, fused, defer in (("per_level", False, False), ("fused", True, False), ("fused_deferred", True, True)):
+from lcrec_b200.optim import FusedAdam
+for name, fused, defer, fopt in (("per_level", False, False, False), ("fused_deferred", True, True, False),
+                                 ("fused_deferred_fusedopt", True, True, True)):
     torch.manual_seed(0)
     m = RQVAE(in_dim=4096, num_emb_list=[256] * 4, e_dim=32, layers=dims, sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50).to(dev).train()
-    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt = (FusedAdam if fopt else torch.optim.AdamW)(m.parameters(), lr=1e-3, weight_decay=1e-4)
     RQ.FUSED_TRAIN = fused
 
     def step(i):
@@ -23,8 +25,11 @@ for name, fused, defer in (("per_level", False, False), ("fused", True, False), 
         o, rq_loss, idx = m(xb, use_sk=True)
         loss, rec = m.compute_loss(o, rq_loss, xs=xb)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
-        opt.step()
+        if fopt:
+            opt.clip_and_step(1.0)
+        else:
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
         return loss
 
     def run(i):
