@@ -13,6 +13,15 @@ import torch
 from . import _lib
 
 
+def _bump_versions(tensors) -> None:
+    """The kernel writes the parameters through raw pointers; consumers that cache derived data by ``Tensor._version``
+    (MLPLayers keeps split copies of its weights) must see an in-place update, exactly as after torch.optim's ``add_``."""
+    try:
+        torch._C._autograd._unsafe_set_version_counter(tuple(tensors), tuple(t._version + 1 for t in tensors))
+    except (AttributeError, TypeError, RuntimeError):
+        torch._foreach_add_(list(tensors), 0.0)
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled_weight_decay=decoupled, amsgrad=False,
@@ -74,6 +83,7 @@ class FusedAdam(torch.optim.Optimizer):
                     float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(bool(group.get("decoupled_weight_decay", True))),
                     steps.pop(), float(max_norm), 1, C.c_void_p(0 if norm_out is None else norm_out.data_ptr()),
                     C.c_void_p(self._ws.data_ptr()), self._ws.numel(), stream))
+                _bump_versions(ps)
         return norm_out
 
     @torch.no_grad()

@@ -40,12 +40,13 @@ def test_fused_adam_matches_torch(decoupled, wd, max_norm, scale):
             ours.step()
         for i, (a, b) in enumerate(zip(pa, pb)):
             np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-5, atol=0, err_msg=f"grad {i}")
-            np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-5, atol=1e-7, err_msg=f"p {i}")
+            np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-5, atol=5e-6, err_msg=f"p {i}")    # atol: 0.5 % of one lr-sized step (cancellation in g + wd p)
             if a.numel():
                 sa, sb = ours.state[a], ref.state[b]
                 np.testing.assert_allclose(sa["exp_avg"].cpu().numpy(), sb["exp_avg"].cpu().numpy(), rtol=1e-5, atol=1e-9)
                 np.testing.assert_allclose(sa["exp_avg_sq"].cpu().numpy(), sb["exp_avg_sq"].cpu().numpy(), rtol=1e-5, atol=1e-12)
                 assert float(sa["step"]) == float(sb["step"]) == step + 1
+                assert a._version > step                       # in-place update is visible to version-keyed caches
 
 
 def test_fused_adam_state_dict_exchange_and_scheduler():
@@ -63,7 +64,8 @@ def test_fused_adam_state_dict_exchange_and_scheduler():
     with torch.no_grad():
         for a, b in zip(pa, pb):
             a.copy_(b)
-    ours.load_state_dict(ref.state_dict())
+    import copy
+    ours.load_state_dict(copy.deepcopy(ref.state_dict()))         # (torch hands out references to its own state tensors)
     assert ours.param_groups[0]["lr"] == 1e-3 and ours.param_groups[0]["weight_decay"] == 1e-4
     sched_a = torch.optim.lr_scheduler.LambdaLR(ours, lambda i: 0.5 ** i)
     sched_b = torch.optim.lr_scheduler.LambdaLR(ref, lambda i: 0.5 ** i)
@@ -74,7 +76,7 @@ def test_fused_adam_state_dict_exchange_and_scheduler():
     for a, b in zip(pa, pb):
         np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
     back = torch.optim.AdamW(pb, lr=1e-3)
-    back.load_state_dict(ours.state_dict())                          # and back
+    back.load_state_dict(copy.deepcopy(ours.state_dict()))           # and back
     assert float(back.state[pb[0]]["step"]) == 4.0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cpu = [torch.zeros(3, requires_grad=True)]
