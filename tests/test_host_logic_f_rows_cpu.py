@@ -1,0 +1,155 @@
+"""CPU checks of the host-side mirrors added for the SURVEY 8(f) rows and the training path (no kernels run): interface
+surface of the EMA variant (reference index_improve/), deferred host checks, optimiser selection and state layout, and
+that none of the new operators has a CPU path."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from lcrec_b200 import ops
+from lcrec_b200.index_improve.main import parse_args as parse_args_improve
+from lcrec_b200.index_improve.models import RQVAE as RQVAEImprove
+from lcrec_b200.index_improve.models import ResidualVectorQuantizer as RQImprove
+from lcrec_b200.index_improve.models import VectorQuantizer as VQImprove
+from lcrec_b200.index_improve.trainer import Trainer as TrainerImprove
+from lcrec_b200.models import layers as L
+from lcrec_b200.optim import FusedAdam
+from lcrec_b200.trainer import Trainer
+
+# state_dict keys of the unmodified reference module (index_improve/models/rqvae.py built with two levels, one hidden layer)
+REF_IMPROVE_KEYS = [
+    "encoder.mlp_layers.1.weight", "encoder.mlp_layers.1.bias", "encoder.mlp_layers.4.weight", "encoder.mlp_layers.4.bias",
+    "rq.vq_layers.0._ema_cluster_size", "rq.vq_layers.0._ema_w", "rq.vq_layers.0.embedding.weight",
+    "rq.vq_layers.1._ema_cluster_size", "rq.vq_layers.1._ema_w", "rq.vq_layers.1.embedding.weight",
+    "decoder.mlp_layers.1.weight", "decoder.mlp_layers.1.bias", "decoder.mlp_layers.4.weight", "decoder.mlp_layers.4.bias"]
+
+
+def test_improve_variant_surface():
+    m = RQVAEImprove(in_dim=64, num_emb_list=[8, 8], e_dim=4, layers=[16], sk_epsilons=[0.0, 0.003], ema_decay=0.9,
+                     epsilon=1e-4, reset_threshold=1e-3, reset_interval=7)
+    assert list(m.state_dict().keys()) == REF_IMPROVE_KEYS
+    assert isinstance(m.rq, RQImprove) and all(isinstance(q, VQImprove) for q in m.rq.vq_layers)
+    q = m.rq.vq_layers[1]
+    assert (q.ema_decay, q.epsilon, q.reset_threshold, q.reset_interval, q.step_count) == (0.9, 1e-4, 1e-3, 7, 0)
+    assert q._ema_cluster_size.shape == (8,) and q._ema_w.shape == (8, 4) and float(q._ema_w.abs().sum()) == 0.0
+    assert q.sk_epsilon == 0.003 and q.initted
+    for name in ("forward", "get_indices", "compute_loss", "get_codebook_usage"):
+        assert callable(getattr(m, name))
+    import inspect
+    assert list(inspect.signature(m.forward).parameters) == ["x", "use_sk", "use_ema"]
+    assert list(inspect.signature(q.forward).parameters) == ["x", "use_sk", "use_ema"]
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        q.get_codebook_usage()
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        q.train()(torch.zeros(5, 4))
+
+
+def test_improve_cli_flags():
+    a = parse_args_improve([])
+    assert a.sk_epsilons is None and a.ema_decay == 0.99 and a.epsilon == 1e-5 and a.reset_threshold == 1e-5
+    assert a.reset_interval == 1000 and a.num_emb_list == [256, 256, 256] and a.kmeans_init is True
+    b = parse_args_improve(["--ema_decay", "0.95", "--reset_interval", "10", "--sk_epsilons", "0", "0", "0.003", "--bn", "False"])
+    assert b.ema_decay == 0.95 and b.reset_interval == 10 and b.sk_epsilons == [0.0, 0.0, 0.003] and b.bn is True
+
+
+def _trainer_args(tmp_path, learner="AdamW"):
+    return types.SimpleNamespace(lr=1e-3, learner=learner, lr_scheduler_type="linear", weight_decay=1e-4, epochs=4,
+                                 warmup_epochs=1, save_limit=2, eval_step=2, device="cpu", ckpt_dir=str(tmp_path))
+
+
+def test_trainer_optimizer_selection_and_improve_log(tmp_path):
+    """On a CPU device the Trainer keeps torch.optim (FusedAdam is CUDA only); the variant's trainer passes use_ema and
+    formats the utilisation lines of index_improve/trainer.py:246-253."""
+    m = RQVAEImprove(in_dim=64, num_emb_list=[8, 8], e_dim=4, layers=[16], sk_epsilons=[0.0, 0.0])
+    t = TrainerImprove(_trainer_args(tmp_path), m, data_num=3)
+    assert isinstance(t.optimizer, torch.optim.AdamW) and not isinstance(t.optimizer, FusedAdam)
+    assert isinstance(Trainer(_trainer_args(tmp_path, "sgd"), m, 3).optimizer, torch.optim.SGD)
+    seen = {}
+    m.forward = lambda data, **kw: seen.update(kw) or ("out", "loss", "idx")
+    assert t._model_forward(torch.zeros(1)) == ("out", "loss", "idx") and seen == {"use_ema": True}
+    m.get_codebook_usage = lambda: [{"utilization": 0.5, "used_codes": 4, "total_codes": 8, "quantizer_id": 0},
+                                    {"utilization": 0.25, "used_codes": 2, "total_codes": 8, "quantizer_id": 1}]
+    line = t._generate_valid_output(3, 1.5, 0.125)
+    assert "0.1250" in line and "0.3750" in line and "Quantizer 1: 0.2500 (2/8)" in line and line.endswith("]")
+    base = Trainer(_trainer_args(tmp_path), m, 3)._generate_valid_output(3, 1.5, 0.125)
+    assert "0.125000]" in base and "Quantizer" not in base
+
+
+def test_fused_adam_state_layout_matches_torch():
+    p = [torch.nn.Parameter(torch.zeros(3))]
+    ours, ref = FusedAdam(p, lr=2e-3, weight_decay=1e-4), torch.optim.AdamW(p, lr=2e-3, weight_decay=1e-4)
+    ga, gb = ours.state_dict()["param_groups"][0], ref.state_dict()["param_groups"][0]
+    assert set(ga.keys()) == set(gb.keys())
+    assert all(ga[k] == gb[k] for k in ("lr", "betas", "eps", "weight_decay", "decoupled_weight_decay", "params"))
+    assert FusedAdam(p, decoupled=False).param_groups[0]["decoupled_weight_decay"] is False
+    p[0].grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ours.step()
+    sched = torch.optim.lr_scheduler.LambdaLR(ours, lambda i: 0.5)
+    assert ours.param_groups[0]["lr"] == 1e-3 and sched.get_last_lr() == [1e-3]
+
+
+def test_deferred_checks_queue_and_flush(capsys):
+    bad, ok, nan = torch.tensor([1], dtype=torch.int32), torch.tensor([0], dtype=torch.int32), torch.tensor([1], dtype=torch.int32)
+    ops.check_later("amplitude", ok)
+    with pytest.raises(AssertionError, match="amplitude > 0"):
+        ops.check_later("amplitude", bad)                          # immediate, like the reference's assert (vq.py:59)
+    with pytest.raises(AssertionError):
+        with ops.defer_checks():
+            ops.check_later("amplitude", bad)
+            ops.check_later("sinkhorn", nan)
+            assert len(ops._PENDING) == 2
+    assert ops._PENDING == []
+    with ops.defer_checks():
+        with ops.defer_checks():                                    # nested: evaluated when the outermost block ends
+            ops.check_later("sinkhorn", nan)
+        assert len(ops._PENDING) == 1
+    assert ops._PENDING == [] and "Sinkhorn Algorithm returns nan/inf values." in capsys.readouterr().out
+    with pytest.raises(ValueError):
+        with ops.defer_checks():
+            ops.check_later("amplitude", bad)
+            raise ValueError("step failed first")
+    assert ops._PENDING == []                                      # nothing leaks into the next step
+    with pytest.raises(RuntimeError, match="peer rank"):
+        ops.check_later("sinkhorn", torch.tensor([8], dtype=torch.int32))
+
+
+def test_new_operators_have_no_cpu_path(tmp_path):
+    x = torch.zeros(4, 8)
+    for call in (lambda: ops.ema_update(x, torch.zeros(4, dtype=torch.int64), torch.zeros(2), torch.zeros(2, 8), torch.zeros(2, 8), 0.99, 1e-5),
+                 lambda: ops.codebook_usage(torch.zeros(4), 1e-5, 1e-5),
+                 lambda: ops.masked_mean_pool(torch.zeros(2, 3, 8), torch.ones(2, 3, dtype=torch.int64)),
+                 lambda: ops.kmeans_center(x),
+                 lambda: ops.kmeans_lloyd(x, x[:2], 5, 1e-4),
+                 lambda: ops.rq_train_forward(x, torch.zeros(4, 1, dtype=torch.int64), [torch.zeros(2, 8)]),
+                 lambda: ops.rq_train_backward(torch.zeros(1, 4, 8), torch.zeros(1, 4, dtype=torch.int64), [2], None, None, 0.25)):
+        with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+            call()
+    old = L.KMEANS_BACKEND
+    try:
+        L.KMEANS_BACKEND = "device"
+        with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+            L.kmeans(x, 2, 5)
+        L.KMEANS_BACKEND = "gpu?"
+        with pytest.raises(ValueError):
+            L.kmeans(x, 2, 5)
+        L.KMEANS_BACKEND = "sklearn"                                # the reference's own call works anywhere
+        np.random.seed(0)
+        c = L.kmeans(torch.randn(64, 8), 4, 5)
+        assert c.shape == (4, 8) and c.dtype == torch.float32
+    finally:
+        L.KMEANS_BACKEND = old
+    from lcrec_b200.text_emb import generate_item_embedding
+    args = types.SimpleNamespace(root=str(tmp_path), dataset="Toy", plm_name="p", max_sent_len=8, device="cpu")
+    tok = lambda *a, **k: _Enc()                                    # noqa: E731
+
+    class _Enc(dict):
+        def __init__(self):
+            super().__init__(input_ids=torch.ones(1, 3, dtype=torch.int64), attention_mask=torch.ones(1, 3, dtype=torch.int64))
+        to = lambda self, device: self                              # noqa: E731
+        input_ids = property(lambda self: self["input_ids"])
+        attention_mask = property(lambda self: self["attention_mask"])
+    model = lambda input_ids, attention_mask: types.SimpleNamespace(last_hidden_state=torch.zeros(1, 3, 8))   # noqa: E731
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        generate_item_embedding(args, [[0, ["a b", "c"]]], tok, model)
