@@ -150,3 +150,30 @@ def test_ema_rqvae_training_step_and_state_dict():
     assert all(torch.equal(a, q.embedding.weight.detach()) for a, q in zip(snap, m.rq.vq_layers))
     stats = m.get_codebook_usage()
     assert [s["quantizer_id"] for s in stats] == [0, 1, 2] and all(0 < s["used_codes"] <= 32 for s in stats)
+
+
+def test_improve_trainer_matches_reference_losses(golden, tmp_path):
+    """Loss trajectory of the UNMODIFIED index_improve Trainer._train_epoch (oracle/make_golden_ema_trainer.py: 4 epochs x 4
+    batches, AdamW + linear warm-up + clip 1.0, EMA step every batch, Sinkhorn on the last level) from the same initial
+    state; collision rate and codebook utilisation after training."""
+    import argparse
+    from lcrec_b200.index_improve.trainer import Trainer
+    g = golden("ema_trainer_steps")
+    args = argparse.Namespace(lr=1e-3, epochs=4, batch_size=256, num_workers=0, eval_step=50, learner="AdamW",
+                              lr_scheduler_type="linear", warmup_epochs=1, data_path="", weight_decay=1e-4,
+                              dropout_prob=0.0, bn=False, loss_type="mse", kmeans_init=False, kmeans_iters=10,
+                              sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50, device="cuda:0", num_emb_list=[32] * 4, e_dim=16,
+                              quant_loss_weight=1.0, beta=0.25, layers=[64, 48], save_limit=5, ckpt_dir=str(tmp_path),
+                              ema_decay=0.99, epsilon=1e-5, reset_threshold=1e-5, reset_interval=1000)
+    m = RQVAE(in_dim=96, num_emb_list=args.num_emb_list, e_dim=16, layers=args.layers, kmeans_init=False,
+              sk_epsilons=args.sk_epsilons, sk_iters=50)
+    m.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("init/")})
+    loader = torch.utils.data.DataLoader(torch.from_numpy(g["x"]), batch_size=256, shuffle=False)
+    tr = Trainer(args, m, len(loader))
+    losses = [tr._train_epoch(loader, ep) for ep in range(4)]
+    np.testing.assert_allclose(np.array(losses), g["losses"], rtol=2e-3)
+    assert abs(tr._valid_epoch(loader) - float(g["collision_rate"])) < 0.02
+    avg, stats = tr._get_codebook_utilization()
+    assert abs(avg - float(g["avg_utilization"])) <= 0.05
+    assert all(abs(s["used_codes"] - int(u)) <= 2 for s, u in zip(stats, g["used_codes"]))
+    assert all(q.step_count == 16 for q in m.rq.vq_layers)
