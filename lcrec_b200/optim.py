@@ -32,7 +32,7 @@ class FusedAdam(torch.optim.Optimizer):
     def clip_and_step(self, max_norm: float = 0.0, want_norm: bool = False):
         """Gradient clipping to ``max_norm`` (<= 0: none) over ALL parameter groups (like ``clip_grad_norm_`` on
         ``model.parameters()``) followed by the update.  Returns the total gradient norm (a device tensor) if asked."""
-        lib = _lib.load()
+        self._opt_called = True          # what the step wrapper of an LR scheduler records (its call-order warning)
         groups = []
         all_grads = []
         for group in self.param_groups:
@@ -52,6 +52,7 @@ class FusedAdam(torch.optim.Optimizer):
             all_grads += [p.grad for p in ps]
         if not all_grads:
             return None
+        lib = _lib.load()
         dev = all_grads[0].device
         norm_out = torch.zeros(1, dtype=torch.float32, device=dev) if (want_norm and max_norm > 0) else None
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

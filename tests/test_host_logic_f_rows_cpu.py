@@ -153,3 +153,41 @@ def test_new_operators_have_no_cpu_path(tmp_path):
     model = lambda input_ids, attention_mask: types.SimpleNamespace(last_hidden_state=torch.zeros(1, 3, 8))   # noqa: E731
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         generate_item_embedding(args, [[0, ["a b", "c"]]], tok, model)
+
+
+def test_rq_training_backward_formulas_match_autograd():
+    """The analytic gradients lcrec_rq_train_backward implements (include/lcrec_b200.h), evaluated here with plain torch on
+    the CPU, against autograd through the reference's own per-level expressions (vq.py:87-99, rq.py:39-56) for fixed codes:
+    d x_q / d z = I, only level 0's commitment term reaches z, codebooks receive the codebook-loss term."""
+    torch.manual_seed(0)
+    n, d, ks, beta = 50, 6, [7, 5, 9], 0.25
+    z = torch.randn(n, d, dtype=torch.float64, requires_grad=True)
+    cbs = [torch.randn(k, d, dtype=torch.float64, requires_grad=True) for k in ks]
+    codes = torch.stack([torch.randint(0, k, (n,)) for k in ks], dim=1)
+    w = torch.randn(n, d, dtype=torch.float64)
+    residual, x_q, losses, diffs = z, 0, [], []
+    for l, cb in enumerate(cbs):
+        q = cb[codes[:, l]]
+        diffs.append((q - residual).detach())
+        loss = torch.nn.functional.mse_loss(q, residual.detach()) + beta * torch.nn.functional.mse_loss(q.detach(), residual)
+        x_res = residual + (q - residual).detach()
+        residual = residual - x_res
+        x_q = x_q + x_res
+        losses.append(loss)
+    mean_loss = torch.stack(losses).mean()
+    g_loss = 3.0
+    ((x_q * w).sum() + g_loss * mean_loss).backward()
+    per_elem = 2.0 / (n * d) / len(ks)
+    np.testing.assert_allclose(z.grad.numpy(), (w - g_loss * beta * per_elem * diffs[0]).numpy(), rtol=1e-12, atol=1e-15)
+    for l, cb in enumerate(cbs):
+        want = torch.zeros_like(cb).index_add_(0, codes[:, l], diffs[l]) * (g_loss * per_elem)
+        np.testing.assert_allclose(cb.grad.numpy(), want.detach().numpy(), rtol=1e-12, atol=1e-15)
+
+
+def test_fused_adam_marks_optimizer_step_for_schedulers(recwarn):
+    p = [torch.nn.Parameter(torch.zeros(3))]
+    opt = FusedAdam(p, lr=1e-3)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda i: 1.0)
+    opt.clip_and_step(1.0)                       # no gradients: nothing to launch, but the call is recorded
+    sched.step()
+    assert not [w for w in recwarn.list if "lr_scheduler.step()" in str(w.message)]
