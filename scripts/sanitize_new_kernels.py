@@ -1,5 +1,6 @@
-"""One small invocation of every kernel added for the SURVEY 8(f) rows and the training path, for
-`compute-sanitizer --tool memcheck --error-exitcode 3 python scripts/sanitize_new_kernels.py`."""
+"""One small invocation of every kernel added for the SURVEY 8(f) rows and the training path (odd sizes, empty tensors, list
+flushes, sequence splits, relocation) - a quick crash test on a GPU box.  compute-sanitizer is closed on this pool
+(`gpurun_out/sanitize_new.log`), so bounds are covered by the parity tests at ragged shapes instead."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
