@@ -1,0 +1,125 @@
+"""Data-parallel training of the RQ-VAE over the GPUs of one box ("Training DP").
+
+The reference's ``index/trainer.py`` is single-device; the parity target is therefore the single-device step on the GLOBAL
+batch.  One process per GPU (``torch.distributed``, NCCL over NVLink), model replicated, every rank reads the same global
+batches (same loader, same shuffle seed) and takes a contiguous row block of each (``ShardPlan``).  Per step, exactly two
+things cross NVLink, as the north star asks:
+
+* the Sinkhorn level is ONE (global batch x K) problem (``vq.py:77-79``): ``DistributedSinkhorn`` keeps the row steps local
+  and all-reduces the column marginals inside the kernel through peer memory (plus one 2-element MAX all-reduce for the
+  centring of ``vq.py:54-55``);
+* the gradients: every loss of the step is a mean over batch rows, so rank r back-propagates ``loss_r * n_r / N`` and ONE
+  ``all_reduce(SUM)`` over a flat bucket that holds every gradient (encoder + decoder 89.5 MB, codebooks 128 KB) yields the
+  gradient of the global-batch loss on every rank; clipping and the optimiser step then run identically everywhere
+  (``lcrec_adam_clip_step``), so the replicas never diverge.
+
+Codebook k-means initialisation (first batch, ``vq.py:67-68``) runs on the full global batch on every rank with the same
+numpy seed.  BatchNorm in training mode would need synchronised batch statistics and is refused.  Rank 0 writes checkpoints.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from tqdm import tqdm
+
+from . import ops
+from .distributed import ShardPlan
+from .optim import FusedAdam
+from .trainer import Trainer
+from .utils import set_color
+
+
+class DataParallelTrainer(Trainer):
+    def __init__(self, args, model, data_num, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("DataParallelTrainer needs an initialised torch.distributed process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in model.modules()):
+            raise NotImplementedError("data-parallel training with BatchNorm needs synchronised batch statistics "
+                                      "(the single-device global-batch semantics of the reference); use bn=False")
+        super().__init__(args, model, data_num)
+        self._flat = None
+        self._flat_params = None
+        for p in self.model.parameters():                       # identical replicas whatever the local seed was
+            dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0,
+                           group=self.group)
+        if self.device.type == "cuda":
+            self._hook_distributed_sinkhorn()
+
+    # ---- the Sinkhorn level as one global problem
+    def _hook_distributed_sinkhorn(self):
+        from .distributed import DistributedSinkhorn
+        rq = getattr(self.model, "rq", None)
+        for q in (rq.vq_layers if rq is not None else []):
+            if getattr(q, "sk_epsilon", 0) and q.sk_epsilon > 0 and getattr(q, "dist_sinkhorn", None) is None:
+                q.dist_sinkhorn = DistributedSinkhorn(q.n_e, self.device, self.group)
+
+    # ---- one all-reduce over every gradient
+    def _all_reduce_grads(self):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        if self._flat is None or self._flat_params != [id(p) for p in params]:
+            total = sum(p.numel() for p in params)
+            self._flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self._flat_params = [id(p) for p in params]
+        flat, views, off = self._flat, [], 0
+        for p in params:
+            views.append(flat[off: off + p.numel()].view_as(p))
+            off += p.numel()
+        have = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
+        miss = [v for v, p in zip(views, params) if p.grad is None]
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v in miss:                                          # a rank without rows contributes zeros
+            v.zero_()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        for p, v in zip(params, views):                         # gradients now live in the bucket (no copy back)
+            p.grad = v
+
+    def _init_codebooks_on_global_batch(self, data):
+        rq = getattr(self.model, "rq", None)
+        if rq is None or not any(not q.initted for q in rq.vq_layers):
+            return
+        with torch.no_grad():                                   # same rows, same numpy RNG state on every rank
+            self._model_forward(data.to(self.device))
+
+    def _train_epoch(self, train_data, epoch_idx):
+        self.model.train()
+        total_loss = 0
+        total_recon_loss = 0
+        bar = tqdm(train_data, total=len(train_data), ncols=100, desc=set_color(f"Train {epoch_idx}", "pink"),
+                   disable=self.rank != 0)
+        for data in bar:
+            n = data.shape[0]
+            plan = ShardPlan(n, self.world)
+            local = data[plan.slice(self.rank)].to(self.device)
+            weight = local.shape[0] / max(n, 1)
+            with ops.defer_checks():
+                self.optimizer.zero_grad()
+                self._init_codebooks_on_global_batch(data)
+                stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+                if local.shape[0] > 0:
+                    out, rq_loss, _ = self._model_forward(local)
+                    loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=local)
+                    (loss * weight).backward()
+                    stats = torch.stack([loss.detach(), loss_recon.detach()]).float() * weight
+                self._all_reduce_grads()
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)     # the global-batch loss values
+                self._check_nan(stats[0])
+                if isinstance(self.optimizer, FusedAdam):
+                    self.optimizer.clip_and_step(1.0)
+                else:
+                    torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
+                    self.optimizer.step()
+                self.scheduler.step()
+                total_loss += stats[0].item()
+                total_recon_loss += stats[1].item()
+        return total_loss, total_recon_loss
+
+    def _save_checkpoint(self, epoch, collision_rate=1, ckpt_file=None):
+        if self.rank != 0:
+            import os
+            name = ckpt_file if ckpt_file else "epoch_%d_collision_%.4f_model.pth" % (epoch, collision_rate)
+            return os.path.join(self.ckpt_dir, name)
+        return super()._save_checkpoint(epoch, collision_rate=collision_rate, ckpt_file=ckpt_file)

@@ -2,6 +2,7 @@
 ``type=bool`` quirk for --bn / --kmeans_init (any non-empty string, e.g. ``--bn False``, is True)."""
 import argparse
 import logging
+import os
 import random
 
 import numpy as np
@@ -62,7 +63,18 @@ def main(argv=None):
                   kmeans_iters=args.kmeans_iters, sk_epsilons=args.sk_epsilons, sk_iters=args.sk_iters)
     print(model)
     loader = DataLoader(data, num_workers=args.num_workers, batch_size=args.batch_size, shuffle=True, pin_memory=True)
-    best_loss, best_collision_rate = Trainer(args, model, len(loader)).fit(loader)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:      # torchrun: one process per GPU, every rank reads the same batches and trains its row block of each
+        import torch.distributed as dist
+        from .dp_trainer import DataParallelTrainer
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        args.device = f"cuda:{local_rank}"
+        dist.init_process_group("nccl")
+        trainer = DataParallelTrainer(args, model, len(loader))
+    else:
+        trainer = Trainer(args, model, len(loader))
+    best_loss, best_collision_rate = trainer.fit(loader)
     print("Best Loss", best_loss)
     print("Best Collision Rate", best_collision_rate)
 
