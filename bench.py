@@ -183,7 +183,7 @@ def run_reference_arm(a):
     if rank != 0:
         return 0
     ws, bs, cbs, head = make_model()
-    n_sample = a.cpu_sample
+    n_sample = min(a.cpu_sample or 2048, HEAD_ITEMS)
     vals = []
     for i in range(a.warmup + a.steps):
         v, dt, st = cpu_sample_run(ws, bs, cbs, head, n_sample)
@@ -353,9 +353,10 @@ def run_gpu_arm(a):
                 "hbm_frac_end_to_end": value / world * BYTES_PER_ITEM / 1e9 / pk["hbm_gbs"], "stage_ms_per_step": stage_ms}
         cpu = None
         if world == 1 and not a.no_cpu:
-            v, dt, st = cpu_sample_run(ws, bs, cbs, head, a.cpu_sample)
+            n_cpu = min(a.cpu_sample or 8192, HEAD_ITEMS)
+            v, dt, st = cpu_sample_run(ws, bs, cbs, head, n_cpu)
             cpu = {"value": v, "unit": "items/s", "cores": host_threads(), "kind": "port", "seconds": dt,
-                   "sample": f"{a.cpu_sample} items of the same stream, full generate_indices incl. per-group re-encoding (numpy/OpenBLAS)"}
+                   "sample": f"{n_cpu} items of the same stream, full generate_indices incl. per-group re-encoding (numpy/OpenBLAS)"}
         line = {"metric": "items indexed/sec (4-level RQ + Sinkhorn collision resolution)", "value": value, "unit": "items/s",
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (low-rank parents + noise, random-init encoder, k-means-style codebooks)",
@@ -379,7 +380,9 @@ def main():
     ap.add_argument("--items", type=int, default=1_000_000, help="items per GPU")
     ap.add_argument("--chunk-rows", dest="chunk_rows", type=int, default=131072)
     ap.add_argument("--e2e-items", dest="e2e_items", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=2048)
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,
+                    help="items of the CPU sample: default 8192 for the cpu_baseline leg of the GPU arm (one run, ~15 s on 16 host "
+                         "threads), 2048 per step for --impl reference (warmup + steps runs)")
     ap.add_argument("--engine", type=int, default=1, choices=[0, 1], help="GEMM operand encoding: 1 = f16 x3 (default), 0 = tf32 x3")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
