@@ -191,3 +191,70 @@ def test_fused_adam_marks_optimizer_step_for_schedulers(recwarn):
     opt.clip_and_step(1.0)                       # no gradients: nothing to launch, but the call is recorded
     sched.step()
     assert not [w for w in recwarn.list if "lr_scheduler.step()" in str(w.message)]
+
+
+def test_producer_host_loop_against_reference_npy(golden, tmp_path, monkeypatch):
+    """Host logic of lcrec_b200.text_emb.generate_item_embedding (item ordering, per-field accumulate / divide, batching,
+    word drop draws, file contract) with the pooling operator replaced by the ORACLE (tests only - the product operator has
+    no CPU path): reproduces the .npy of the unmodified reference producer, also when several items are pooled per call."""
+    import os
+    import random
+    from oracle import lcrec_oracle as O
+    from lcrec_b200 import text_emb
+    g = golden("pool_kat")
+    n, nf = int(g["n_items"]), int(g["n_fields"])
+
+    def oracle_pool(h, mask, out=None, accumulate=False, divide_by=0.0):
+        r = torch.from_numpy(O.masked_mean_pool(h.numpy(), mask.numpy()))
+        if accumulate:
+            r = out + r
+        if divide_by > 0:
+            r = r / divide_by
+        out.copy_(r)
+        return out
+    monkeypatch.setattr(text_emb.ops, "masked_mean_pool", oracle_pool)
+    E, P = torch.from_numpy(g["E"]), torch.from_numpy(g["P"])
+    ids_of = {}                                                     # (item, field) -> recorded token row
+    for i in range(n):
+        for f in range(nf):
+            ids, mask = g[f"ids_{nf * i + f}"], g[f"mask_{nf * i + f}"]
+            ids_of[f"item{i}field{f}"] = ids[0][mask[0] == 1]
+
+    class Enc(dict):
+        to = lambda self, device: self                              # noqa: E731
+        input_ids = property(lambda self: self["input_ids"])
+        attention_mask = property(lambda self: self["attention_mask"])
+
+    def tokenizer(sentences, max_length, truncation, return_tensors, padding):
+        rows = [ids_of[s.split(" ")[0]] for s in sentences]         # first word names the recorded sequence
+        width = (max(len(r) for r in rows) + 7) // 8 * 8
+        ids = torch.zeros(len(rows), width, dtype=torch.int64)
+        mask = torch.zeros(len(rows), width, dtype=torch.int64)
+        for j, r in enumerate(rows):
+            ids[j, : len(r)] = torch.from_numpy(np.asarray(r))
+            mask[j, : len(r)] = 1
+        return Enc(input_ids=ids, attention_mask=mask)
+
+    def model(input_ids, attention_mask):
+        h = E[input_ids] + P[: input_ids.shape[1]][None] + (1 - attention_mask).unsqueeze(-1) * 1e3
+        return types.SimpleNamespace(last_hidden_state=h)
+
+    items = [[i, [f"item{i}field0 x y", f"item{i}field1 z"]] for i in reversed(range(n))]
+    scale = np.abs(g["emb"]).max(axis=1, keepdims=True)
+    for bs in (1, 5):
+        args = types.SimpleNamespace(root=str(tmp_path), dataset=f"Toy{bs}", plm_name="standin", max_sent_len=24, device="cpu")
+        emb = text_emb.generate_item_embedding(args, items, tokenizer, model, word_drop_ratio=-1, batch_size=bs)
+        saved = np.load(os.path.join(str(tmp_path), f"Toy{bs}.emb-standin-td.npy"))
+        assert saved.shape == g["emb"].shape and np.array_equal(saved, emb.numpy())
+        assert (np.abs(saved - g["emb"]) <= 1e-6 * scale).all()
+    # word drop consumes Python's RNG once per word, in order (amazon_text_emb.py:73-85)
+    random.seed(3)
+    expect = [random.random() for _ in range(5)]
+    random.seed(3)
+    seen = []
+    tok2 = lambda sentences, **kw: seen.append(list(sentences)) or tokenizer([f"item0field{len(seen) - 1}"], **kw)   # noqa: E731
+    args = types.SimpleNamespace(root=str(tmp_path), dataset="ToyDrop", plm_name="standin", max_sent_len=24, device="cpu")
+    text_emb.generate_item_embedding(args, [[0, ["a b c", "d e"]]], tok2, model, word_drop_ratio=0.5, save=False)
+    kept = [" ".join(w for w, r in zip("a b c".split(), expect[:3]) if r > 0.5),
+            " ".join(w for w, r in zip("d e".split(), expect[3:]) if r > 0.5)]
+    assert seen == [[kept[0]], [kept[1]]]
