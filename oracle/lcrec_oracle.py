@@ -204,6 +204,58 @@ def vq_forward(x: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: fl
 
 
 # --------------------------------------------------------------------------- #
+# f1: k-means++ seeding of scikit-learn with PRE-DRAWN random numbers (groundwork for a device seeding kernel)
+# --------------------------------------------------------------------------- #
+def kmeanspp_draws(random_state, n_clusters: int):
+    """The random numbers ``sklearn.cluster.kmeans_plusplus`` (1.9.0, `_kmeans_plusplus`) consumes, in its order: one
+    ``random_sample()`` for the first centre (``RandomState.choice(n, p=...)`` draws exactly one uniform), then
+    ``uniform(size=2 + int(log(K)))`` per further centre.  Their number does not depend on the data, so a device seeding
+    kernel can receive them up front and still consume numpy's global RNG exactly like the reference's KMeans.fit."""
+    trials = 2 + int(np.log(n_clusters))
+    u0 = float(random_state.random_sample())
+    return u0, [random_state.uniform(size=trials) for _ in range(1, n_clusters)]
+
+
+def kmeanspp_predrawn(xc: np.ndarray, n_clusters: int, u0: float, draws) -> np.ndarray:
+    """Indices of the seeds `_kmeans_plusplus` picks on the centred fp32 batch ``xc`` with unit sample weights, given the
+    pre-drawn numbers: first centre = searchsorted(cumsum(1/n) / last, u0, 'right') (``RandomState.choice``); then per centre:
+    candidates = searchsorted(fp32 sequential cumsum of the closest squared distances, u * potential), squared distances of
+    the candidates to all rows in fp64 from the up-cast rows (``-2 x.y + |x|^2 + |y|^2``, clipped at 0, rounded to fp32:
+    sklearn's `_euclidean_distances_upcast`), the candidate with the smallest new potential wins (first on ties)."""
+    x32 = np.ascontiguousarray(xc, dtype=F32)
+    n = x32.shape[0]
+    x64 = x32.astype(F64)
+    norms = (x64 * x64).sum(axis=1)
+    ones = np.ones(n, dtype=F32)
+
+    def sqdist(rows):                                   # (len(rows), n) fp32
+        d = -2.0 * (x64[rows] @ x64.T)
+        d += norms[rows][:, None]
+        d += norms[None, :]
+        return np.maximum(d.astype(F32), F32(0))
+
+    p = ones.astype(F64) / F64(ones.sum())
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    first = int(cdf.searchsorted(u0, side="right"))
+    indices = [first]
+    closest = sqdist([first])[0]
+    pot = closest @ ones
+    for u in draws:
+        rand_vals = u * pot
+        cand = np.searchsorted(np.cumsum(ones * closest), rand_vals)
+        np.clip(cand, None, n - 1, out=cand)
+        dc = sqdist(cand)
+        np.minimum(closest, dc, out=dc)
+        cand_pot = dc @ ones.reshape(-1, 1)
+        best = int(np.argmin(cand_pot))
+        pot = cand_pot[best]
+        closest = dc[best]
+        indices.append(int(cand[best]))
+    return np.asarray(indices, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------- #
 # f3: index_improve EMA codebook update, usage statistics, dead-code reset
 # --------------------------------------------------------------------------- #
 def _fma32(a, b, c):

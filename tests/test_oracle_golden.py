@@ -151,3 +151,23 @@ def test_masked_mean_pool_matches_reference_producer(golden):
         assert any((m == 0).any() for m in ms) or i > 0
         e = O.item_embedding(hs, ms)[0]
         assert np.abs(e - g["emb"][i]).max() <= 1e-6 * np.abs(g["emb"][i]).max()
+
+
+# ------------------------------------------------------------------ f1: k-means++ seeding with pre-drawn random numbers
+@pytest.mark.parametrize("n,d,k,seed", [(1024, 32, 256, 0), (600, 100, 20, 1), (2000, 16, 64, 2)])
+def test_kmeanspp_with_predrawn_numbers_equals_sklearn(n, d, k, seed):
+    """The oracle's restatement of scikit-learn's k-means++ (the third-party routine behind layers.py:69-82, pinned 1.9.0)
+    picks the same seeds when it is handed the random numbers up front, and leaves numpy's global RNG in the same state:
+    the seeding can move to the device without changing what the reference's KMeans.fit would draw."""
+    from sklearn.cluster import kmeans_plusplus
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((n, d)) * 0.5 + 1.0).astype(np.float32)
+    xc = x - x.mean(axis=0)
+    np.random.seed(2024 + seed)
+    _, want = kmeans_plusplus(xc, k)
+    state_after = np.random.random_sample()
+    np.random.seed(2024 + seed)
+    u0, draws = O.kmeanspp_draws(np.random.mtrand._rand, k)
+    assert np.random.random_sample() == state_after
+    got = O.kmeanspp_predrawn(xc, k, u0, draws)
+    assert np.array_equal(got, want)
