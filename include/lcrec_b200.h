@@ -293,6 +293,16 @@ int lcrec_kmeans_center(const float* x, int64_t n, int e_dim, float* xc, float* 
 int lcrec_kmeans_lloyd(const float* xc, int64_t n, int e_dim, float* centers, int n_codes, int max_iter, double tol,
                        const float* add_mean, int64_t* labels_out, double* inertia_host, int* n_iter_host,
                        void* workspace, int64_t workspace_bytes, void* stream);
+/* k-means++ seeding with scikit-learn's arithmetic from random numbers drawn up front (sklearn `_kmeans_plusplus`: one
+ * uniform for the first centre - the caller turns it into first_index exactly like RandomState.choice - then n_trials =
+ * 2 + int(log(K)) uniforms per further centre; `draws` is a DEVICE array of (n_clusters - 1) x n_trials doubles in drawing
+ * order).  xc: centred rows (n, e_dim); indices (n_clusters int64, device) receives the chosen rows, centers (nullable)
+ * their vectors.  No host read inside: three launches per centre are enqueued back to back.
+ * NOT YET RUN ON HARDWARE in round 1 (restated and pinned on the CPU: oracle.kmeanspp_predrawn). */
+int64_t lcrec_kmeanspp_workspace_bytes(int64_t n, int n_trials);
+int lcrec_kmeanspp_seed(const float* xc, int64_t n, int e_dim, int n_clusters, int64_t first_index, const double* draws,
+                        int n_trials, int64_t* indices, float* centers, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 /* ---- f3: EMA codebook variant (index_improve/models/vq.py) ----------------------------------
  * lcrec_ema_update: the `self.training and use_ema` block of the improved VectorQuantizer.forward
  * (index_improve/models/vq.py:146-187) in place on the module's buffers: per-code counts of `indices` (n,) int64,

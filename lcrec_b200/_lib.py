@@ -88,6 +88,8 @@ SIGNATURES = {
     "lcrec_adam_workspace_bytes": (i64, [C.c_int, C.POINTER(i64)]),
     "lcrec_adam_clip_step": (C.c_int, [C.c_int, pp, pp, pp, pp, C.POINTER(i64), f64, f64, f64, f64, f64, C.c_int, i64, f64,
                                        C.c_int, vp, vp, i64, vp]),
+    "lcrec_kmeanspp_workspace_bytes": (i64, [i64, C.c_int]),
+    "lcrec_kmeanspp_seed": (C.c_int, [vp, i64, C.c_int, C.c_int, i64, vp, C.c_int, vp, vp, vp, i64, vp]),
     "lcrec_indexer_codes": (vp, [vp]),
     "lcrec_indexer_resid": (vp, [vp]),
 }

@@ -230,13 +230,35 @@ def kmeans(samples, num_clusters, num_iters=10):
         x = samples.detach().cpu().numpy()
         fit = KMeans(n_clusters=num_clusters, max_iter=num_iters).fit(x)
         return torch.from_numpy(fit.cluster_centers_).to(samples.device)
-    if KMEANS_BACKEND != "device":
+    if KMEANS_BACKEND not in ("device", "device_seed"):
         raise ValueError(f"unknown k-means backend {KMEANS_BACKEND!r}")
-    from sklearn.cluster import kmeans_plusplus
     xc, mean, mean_var = ops.kmeans_center(samples.detach())
-    seeds, _ = kmeans_plusplus(xc.cpu().numpy(), num_clusters)
-    fit = ops.kmeans_lloyd(xc, torch.from_numpy(seeds).to(xc.device), num_iters, 1e-4 * mean_var, add_mean=mean)
+    if KMEANS_BACKEND == "device":
+        from sklearn.cluster import kmeans_plusplus
+        seeds, _ = kmeans_plusplus(xc.cpu().numpy(), num_clusters)
+        seeds = torch.from_numpy(seeds).to(xc.device)
+    else:
+        # "device_seed" (not yet run on hardware in round 1): the seeding on the device as well; the host only DRAWS the
+        # random numbers, in sklearn's order, from numpy's global RNG (their count does not depend on the data)
+        first, draws = kmeanspp_random_numbers(xc.shape[0], num_clusters)
+        _, seeds = ops.kmeanspp_seed(xc, num_clusters, first, torch.from_numpy(draws))
+    fit = ops.kmeans_lloyd(xc, seeds, num_iters, 1e-4 * mean_var, add_mean=mean)
     return fit["centers"]
+
+
+def kmeanspp_random_numbers(n_samples, num_clusters):
+    """What ``sklearn.cluster.kmeans_plusplus`` draws from numpy's global RNG, in its order: the first centre through
+    ``RandomState.choice(n, p=uniform)`` (one uniform -> searchsorted on the normalised cumulative weights, side 'right'),
+    then ``uniform(size=2 + int(log(K)))`` per further centre.  Returns (first index, (K-1, trials) fp64)."""
+    import numpy as np
+    rs = np.random.mtrand._rand
+    trials = 2 + int(np.log(num_clusters))
+    p = np.ones(n_samples, dtype=np.float32).astype(np.float64) / np.float64(np.float32(n_samples))
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    first = int(cdf.searchsorted(rs.random_sample(), side="right"))
+    draws = np.stack([rs.uniform(size=trials) for _ in range(1, num_clusters)]) if num_clusters > 1 else np.zeros((0, trials))
+    return first, draws
 
 
 @torch.no_grad()

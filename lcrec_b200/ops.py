@@ -357,6 +357,24 @@ def kmeans_center(x: torch.Tensor):
     return xc, mean, float(var.value)
 
 
+def kmeanspp_seed(xc: torch.Tensor, n_clusters: int, first_index: int, draws: torch.Tensor):
+    """k-means++ seeds of sklearn's `_kmeans_plusplus` on centred rows from pre-drawn uniforms (``draws``: (K-1, trials)
+    fp64).  Returns (indices (K,) int64, centers (K, D))."""
+    _need_cuda(xc)
+    lib = _lib.load()
+    x2 = _f32c(xc)
+    n, d = x2.shape
+    dr = draws.detach().to(device=x2.device, dtype=torch.float64).contiguous().reshape(max(n_clusters - 1, 0), -1)
+    trials = int(dr.shape[1]) if dr.numel() else 1
+    idx = torch.empty(n_clusters, dtype=torch.int64, device=x2.device)
+    centers = torch.empty((n_clusters, d), dtype=torch.float32, device=x2.device)
+    ws = _ws(lib.lcrec_kmeanspp_workspace_bytes(n, trials), x2.device)
+    with torch.cuda.device(x2.device):
+        _lib.check(lib.lcrec_kmeanspp_seed(_p(x2), n, d, int(n_clusters), int(first_index), _p(dr) if dr.numel() else None,
+                                           trials, _p(idx), _p(centers), _p(ws), ws.numel(), _stream(x2)))
+    return idx, centers
+
+
 def kmeans_lloyd(xc: torch.Tensor, seeds: torch.Tensor, max_iter: int, tol: float, add_mean: Optional[torch.Tensor] = None):
     """Lloyd iterations from ``seeds`` on centred data -> dict(centers, labels, inertia, n_iter) (sklearn semantics)."""
     _need_cuda(xc, seeds, add_mean)

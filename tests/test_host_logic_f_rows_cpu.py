@@ -258,3 +258,27 @@ def test_producer_host_loop_against_reference_npy(golden, tmp_path, monkeypatch)
     kept = [" ".join(w for w, r in zip("a b c".split(), expect[:3]) if r > 0.5),
             " ".join(w for w, r in zip("d e".split(), expect[3:]) if r > 0.5)]
     assert seen == [[kept[0]], [kept[1]]]
+
+
+def test_kmeanspp_random_numbers_follow_sklearn():
+    """Host half of the device seeding: the first centre and the per-centre uniforms are what sklearn's kmeans_plusplus
+    consumes from numpy's global RNG (same first index, same RNG state afterwards), independent of the data."""
+    from sklearn.cluster import kmeans_plusplus
+    from lcrec_b200.models.layers import kmeanspp_random_numbers
+    from oracle import lcrec_oracle as O
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((700, 12)).astype(np.float32)
+    xc = x - x.mean(axis=0)
+    np.random.seed(11)
+    _, want = kmeans_plusplus(xc, 40)
+    after = np.random.random_sample()
+    np.random.seed(11)
+    first, draws = kmeanspp_random_numbers(700, 40)
+    assert np.random.random_sample() == after and first == want[0] and draws.shape == (39, 2 + int(np.log(40)))
+    # the oracle's restatement, fed with these numbers, reproduces every seed
+    p = np.ones(700, dtype=np.float64) / 700.0
+    cdf = p.cumsum(); cdf /= cdf[-1]
+    np.random.seed(11)
+    u0, dr = O.kmeanspp_draws(np.random.mtrand._rand, 40)
+    assert int(cdf.searchsorted(u0, side="right")) == first and all(np.array_equal(a, b) for a, b in zip(dr, draws))
+    assert np.array_equal(O.kmeanspp_predrawn(xc, 40, u0, dr), want)
