@@ -8,18 +8,21 @@ from .rq import ResidualVectorQuantizer
 
 
 class RQVAE(_BaseRQVAE):
+    _RQ = ResidualVectorQuantizer
+
     def __init__(self, in_dim=768, num_emb_list=None, e_dim=64, layers=None, dropout_prob=0.0, bn=False,
                  loss_type="mse", quant_loss_weight=1.0, beta=0.25, kmeans_init=False, kmeans_iters=100,
                  sk_epsilons=None, sk_iters=100, ema_decay=0.99, epsilon=1e-5, reset_threshold=1e-5,
                  reset_interval=1000):
+        self._ema_cfg = dict(ema_decay=ema_decay, epsilon=epsilon, reset_threshold=reset_threshold,
+                             reset_interval=reset_interval)
         super().__init__(in_dim=in_dim, num_emb_list=num_emb_list, e_dim=e_dim, layers=layers,
                          dropout_prob=dropout_prob, bn=bn, loss_type=loss_type, quant_loss_weight=quant_loss_weight,
                          beta=beta, kmeans_init=kmeans_init, kmeans_iters=kmeans_iters, sk_epsilons=sk_epsilons,
                          sk_iters=sk_iters)
-        self.rq = ResidualVectorQuantizer(num_emb_list, e_dim, beta=beta, kmeans_init=kmeans_init,
-                                          kmeans_iters=kmeans_iters, sk_epsilons=sk_epsilons, sk_iters=sk_iters,
-                                          ema_decay=ema_decay, epsilon=epsilon, reset_threshold=reset_threshold,
-                                          reset_interval=reset_interval)
+
+    def _quantizer(self, **extra):
+        return super()._quantizer(**self._ema_cfg, **extra)      # the EMA-aware ResidualVectorQuantizer of this package
 
     def forward(self, x, use_sk=True, use_ema=True):
         z = self.encoder(x)

@@ -14,33 +14,26 @@ from .models.rqvae import RQVAE
 from .trainer import Trainer
 
 
+# flag, type, default - the command line of index/main.py:15-47; ``bool`` keeps the reference's quirk (any non-empty string,
+# "False" included, parses to True); list defaults mean nargs="+"
+FLAGS = [
+    ("lr", float, 1e-3), ("epochs", int, 5000), ("batch_size", int, 2048), ("num_workers", int, 4), ("eval_step", int, 50),
+    ("learner", str, "AdamW"), ("lr_scheduler_type", str, "constant"), ("warmup_epochs", int, 50),
+    ("data_path", str, "../data/Games/Games.emb-llama-td.npy"), ("weight_decay", float, 0.0), ("dropout_prob", float, 0.0),
+    ("bn", bool, False), ("loss_type", str, "mse"), ("kmeans_init", bool, True), ("kmeans_iters", int, 100),
+    ("sk_epsilons", float, [0.0, 0.0, 0.0]), ("sk_iters", int, 50), ("device", str, "cuda:0"),
+    ("num_emb_list", int, [256, 256, 256]), ("e_dim", int, 32), ("quant_loss_weight", float, 1.0), ("beta", float, 0.25),
+    ("layers", int, [2048, 1024, 512, 256, 128, 64]), ("save_limit", int, 5), ("ckpt_dir", str, ""),
+]
+
+
 def build_parser(description="Index"):
     p = argparse.ArgumentParser(description=description)
-    p.add_argument("--lr", type=float, default=1e-3)
-    p.add_argument("--epochs", type=int, default=5000)
-    p.add_argument("--batch_size", type=int, default=2048)
-    p.add_argument("--num_workers", type=int, default=4)
-    p.add_argument("--eval_step", type=int, default=50)
-    p.add_argument("--learner", type=str, default="AdamW")
-    p.add_argument("--lr_scheduler_type", type=str, default="constant")
-    p.add_argument("--warmup_epochs", type=int, default=50)
-    p.add_argument("--data_path", type=str, default="../data/Games/Games.emb-llama-td.npy")
-    p.add_argument("--weight_decay", type=float, default=0.0)
-    p.add_argument("--dropout_prob", type=float, default=0.0)
-    p.add_argument("--bn", type=bool, default=False)
-    p.add_argument("--loss_type", type=str, default="mse")
-    p.add_argument("--kmeans_init", type=bool, default=True)
-    p.add_argument("--kmeans_iters", type=int, default=100)
-    p.add_argument("--sk_epsilons", type=float, nargs="+", default=[0.0, 0.0, 0.0])
-    p.add_argument("--sk_iters", type=int, default=50)
-    p.add_argument("--device", type=str, default="cuda:0")
-    p.add_argument("--num_emb_list", type=int, nargs="+", default=[256, 256, 256])
-    p.add_argument("--e_dim", type=int, default=32)
-    p.add_argument("--quant_loss_weight", type=float, default=1.0)
-    p.add_argument("--beta", type=float, default=0.25)
-    p.add_argument("--layers", type=int, nargs="+", default=[2048, 1024, 512, 256, 128, 64])
-    p.add_argument("--save_limit", type=int, default=5)
-    p.add_argument("--ckpt_dir", type=str, default="")
+    for name, kind, default in FLAGS:
+        if isinstance(default, list):
+            p.add_argument("--" + name, type=kind, nargs="+", default=default)
+        else:
+            p.add_argument("--" + name, type=kind, default=default)
     return p
 
 

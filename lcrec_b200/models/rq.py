@@ -60,6 +60,8 @@ class _RQTrainFn(torch.autograd.Function):
 
 
 class ResidualVectorQuantizer(nn.Module):
+    _LEVEL = VectorQuantizer
+
     def __init__(self, n_e_list, e_dim, sk_epsilons, beta=0.25, kmeans_init=False, kmeans_iters=100, sk_iters=100):
         super().__init__()
         self.n_e_list = n_e_list
@@ -70,9 +72,10 @@ class ResidualVectorQuantizer(nn.Module):
         self.kmeans_iters = kmeans_iters
         self.sk_epsilons = sk_epsilons
         self.sk_iters = sk_iters
+        extra = self.__dict__.get("_level_extra", {})           # set by the EMA subclass before this constructor runs
         self.vq_layers = nn.ModuleList(
-            VectorQuantizer(n_e, e_dim, beta=beta, kmeans_init=kmeans_init, kmeans_iters=kmeans_iters,
-                            sk_epsilon=eps, sk_iters=sk_iters)
+            self._LEVEL(n_e, e_dim, beta=beta, kmeans_init=kmeans_init, kmeans_iters=kmeans_iters,
+                        sk_epsilon=eps, sk_iters=sk_iters, **extra)
             for n_e, eps in zip(n_e_list, sk_epsilons))
 
     def get_codebook(self):
@@ -154,13 +157,15 @@ class ResidualVectorQuantizer(nn.Module):
             return self.quantize_fused(x, use_sk)
         if FUSED_TRAIN and not pending_init and type(self).forward is ResidualVectorQuantizer.forward:
             return _RQTrainFn.apply(x, self, use_sk, *[q.embedding.weight for q in self.vq_layers])
-        all_losses, all_indices = [], []
-        x_q = 0
-        residual = x
-        for quantizer in self.vq_layers:
-            x_res, loss, indices = quantizer(residual, use_sk=use_sk)
-            residual = residual - x_res
-            x_q = x_q + x_res
-            all_losses.append(loss)
-            all_indices.append(indices)
-        return x_q, torch.stack(all_losses).mean(), torch.stack(all_indices, dim=-1)
+        return self._forward_levels(x, use_sk=use_sk)
+
+    def _forward_levels(self, x, **level_kwargs):
+        """The reference's chain of level modules (rq.py:45-55): autograd flows through every level."""
+        losses, codes = [], []
+        x_q, residual = 0, x
+        for level in self.vq_layers:
+            x_res, loss, idx = level(residual, **level_kwargs)
+            residual, x_q = residual - x_res, x_q + x_res
+            losses.append(loss)
+            codes.append(idx)
+        return x_q, torch.stack(losses).mean(), torch.stack(codes, dim=-1)

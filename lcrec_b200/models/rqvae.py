@@ -12,30 +12,33 @@ from .rq import ResidualVectorQuantizer
 
 
 class RQVAE(nn.Module):
+    _LOSSES = {"mse": F.mse_loss, "l1": F.l1_loss}
+    _RQ = ResidualVectorQuantizer
+
     def __init__(self, in_dim=768, num_emb_list=None, e_dim=64, layers=None, dropout_prob=0.0, bn=False,
                  loss_type="mse", quant_loss_weight=1.0, beta=0.25, kmeans_init=False, kmeans_iters=100,
                  sk_epsilons=None, sk_iters=100):
         super().__init__()
-        self.in_dim = in_dim
-        self.num_emb_list = num_emb_list
-        self.e_dim = e_dim
-        self.layers = layers
-        self.dropout_prob = dropout_prob
-        self.bn = bn
-        self.loss_type = loss_type
-        self.quant_loss_weight = quant_loss_weight
-        self.beta = beta
-        self.kmeans_init = kmeans_init
-        self.kmeans_iters = kmeans_iters
-        self.sk_epsilons = sk_epsilons
-        self.sk_iters = sk_iters
+        # every constructor argument is kept as an attribute of the same name (generate_indices.py and the checkpoint's
+        # pickled args rely on them)
+        for name, value in dict(in_dim=in_dim, num_emb_list=num_emb_list, e_dim=e_dim, layers=layers,
+                                dropout_prob=dropout_prob, bn=bn, loss_type=loss_type,
+                                quant_loss_weight=quant_loss_weight, beta=beta, kmeans_init=kmeans_init,
+                                kmeans_iters=kmeans_iters, sk_epsilons=sk_epsilons, sk_iters=sk_iters).items():
+            setattr(self, name, value)
+        widths = [in_dim, *layers, e_dim]
+        self.encode_layer_dims, self.decode_layer_dims = widths, widths[::-1]
+        self.encoder = self._stack(widths)
+        self.rq = self._quantizer()
+        self.decoder = self._stack(widths[::-1])
 
-        self.encode_layer_dims = [in_dim] + list(layers) + [e_dim]
-        self.encoder = MLPLayers(layers=self.encode_layer_dims, dropout=dropout_prob, bn=bn)
-        self.rq = ResidualVectorQuantizer(num_emb_list, e_dim, beta=beta, kmeans_init=kmeans_init,
-                                          kmeans_iters=kmeans_iters, sk_epsilons=sk_epsilons, sk_iters=sk_iters)
-        self.decode_layer_dims = self.encode_layer_dims[::-1]
-        self.decoder = MLPLayers(layers=self.decode_layer_dims, dropout=dropout_prob, bn=bn)
+    def _stack(self, widths):
+        return MLPLayers(layers=widths, dropout=self.dropout_prob, bn=self.bn)
+
+    def _quantizer(self, **extra):
+        return self._RQ(self.num_emb_list, self.e_dim, beta=self.beta, kmeans_init=self.kmeans_init,
+                                       kmeans_iters=self.kmeans_iters, sk_epsilons=self.sk_epsilons, sk_iters=self.sk_iters,
+                                       **extra)
 
     def forward(self, x, use_sk=True):
         z = self.encoder(x)
@@ -47,10 +50,8 @@ class RQVAE(nn.Module):
         return self.rq(self.encoder(xs), use_sk=use_sk)[2]
 
     def compute_loss(self, out, quant_loss, xs=None):
-        if self.loss_type == "mse":
-            loss_recon = F.mse_loss(out, xs, reduction="mean")
-        elif self.loss_type == "l1":
-            loss_recon = F.l1_loss(out, xs, reduction="mean")
-        else:
-            raise ValueError("incompatible loss type")
+        recon_fn = self._LOSSES.get(self.loss_type)
+        if recon_fn is None:
+            raise ValueError("incompatible loss type")           # rqvae.py:81
+        loss_recon = recon_fn(out, xs, reduction="mean")
         return loss_recon + self.quant_loss_weight * quant_loss, loss_recon

@@ -282,3 +282,33 @@ def test_kmeanspp_random_numbers_follow_sklearn():
     u0, dr = O.kmeanspp_draws(np.random.mtrand._rand, 40)
     assert int(cdf.searchsorted(u0, side="right")) == first and all(np.array_equal(a, b) for a, b in zip(dr, draws))
     assert np.array_equal(O.kmeanspp_predrawn(xc, 40, u0, dr), want)
+
+
+def test_level_chain_and_factories_with_stub_levels():
+    """The shared per-level loop (rq.py:45-55) on stand-in level modules: residual / x_q bookkeeping, mean of the level
+    losses, stacked codes, keyword pass-through (use_ema) - and the class-level factories the EMA variant overrides."""
+    from lcrec_b200.models import RQVAE, ResidualVectorQuantizer, VectorQuantizer
+
+    class Stub(torch.nn.Module):
+        def __init__(self, k):
+            super().__init__()
+            self.k, self.seen = k, None
+
+        def forward(self, r, use_sk=True, **kw):
+            self.seen = dict(use_sk=use_sk, **kw)
+            return r * 0.5, (r.detach() ** 2).mean() * self.k, torch.full((r.shape[0],), self.k)
+    rq = ResidualVectorQuantizer([4, 4], 3, [0.0, 0.0])
+    assert ResidualVectorQuantizer._LEVEL is VectorQuantizer and RQVAE._RQ is ResidualVectorQuantizer
+    assert RQImprove._LEVEL is VQImprove and RQVAEImprove._RQ is RQImprove
+    rq.vq_layers = torch.nn.ModuleList([Stub(1), Stub(2)])
+    x = torch.ones(2, 3)
+    x_q, loss, idx = rq._forward_levels(x, use_sk=False, use_ema=True)
+    assert torch.allclose(x_q, torch.full((2, 3), 0.75)) and abs(float(loss) - 0.75) < 1e-7
+    assert idx.tolist() == [[1, 2], [1, 2]] and rq.vq_layers[1].seen == {"use_sk": False, "use_ema": True}
+    m = RQVAE(in_dim=10, num_emb_list=[4], e_dim=3, layers=[5], sk_epsilons=[0.0], loss_type="l1")
+    out, xs = torch.zeros(2, 10), torch.ones(2, 10)
+    total, recon = m.compute_loss(out, torch.tensor(0.5), xs=xs)
+    assert float(recon) == 1.0 and float(total) == 1.5
+    m.loss_type = "huber"
+    with pytest.raises(ValueError, match="incompatible loss type"):
+        m.compute_loss(out, torch.tensor(0.5), xs=xs)
