@@ -204,6 +204,40 @@ def vq_forward(x: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: fl
 
 
 # --------------------------------------------------------------------------- #
+# a11: clip_grad_norm_ + Adam / AdamW step (index/trainer.py:49-81, :117-118 -> torch.nn.utils / torch.optim)
+# --------------------------------------------------------------------------- #
+def adam_clip_step(params, grads, exp_avg, exp_avg_sq, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+                   weight_decay: float = 0.0, decoupled: bool = True, max_norm: float = 0.0):
+    """One ``clip_grad_norm_(params, max_norm)`` + ``optimizer.step()`` on lists of fp32 arrays (updated copies returned):
+    total norm over all tensors, coef = min(1, max_norm / (norm + 1e-6)), g *= coef; AdamW: p *= 1 - lr wd / Adam: g += wd p;
+    m += (g - m)(1 - b1); v = v b2 + (1 - b2) g g; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+    ``step`` is the count AFTER this update.  Returns (params, clipped grads, exp_avg, exp_avg_sq, total_norm)."""
+    b1, b2 = betas
+    g = [x.astype(F32, copy=True) for x in grads]
+    norm = F32(np.sqrt(sum(float(np.sum(x.astype(F64) ** 2)) for x in g)))
+    if max_norm > 0:
+        coef = F32(max_norm) / F32(norm + F32(1e-6))
+        coef = coef if coef < 1 else F32(1.0)
+        g = [(x * coef).astype(F32) for x in g]
+    step_size = F32(lr / (1.0 - b1 ** step))
+    bc2_sqrt = F32(np.sqrt(1.0 - b2 ** step))
+    out_p, out_m, out_v = [], [], []
+    for p, gi, m, v in zip(params, g, exp_avg, exp_avg_sq):
+        p = p.astype(F32, copy=True)
+        if decoupled:
+            p = (p * F32(1.0 - lr * weight_decay)).astype(F32)
+            gu = gi
+        else:
+            gu = (gi + F32(weight_decay) * p).astype(F32) if weight_decay != 0 else gi
+        m = (m + (gu - m) * F32(1.0 - b1)).astype(F32)
+        v = (v * F32(b2) + (gu * gu) * F32(1.0 - b2)).astype(F32)
+        denom = (np.sqrt(v) / bc2_sqrt + F32(eps)).astype(F32)
+        p = (p - step_size * (m / denom)).astype(F32)
+        out_p.append(p); out_m.append(m); out_v.append(v)
+    return out_p, g, out_m, out_v, norm
+
+
+# --------------------------------------------------------------------------- #
 # f1: k-means++ seeding of scikit-learn with PRE-DRAWN random numbers (groundwork for a device seeding kernel)
 # --------------------------------------------------------------------------- #
 def kmeanspp_draws(random_state, n_clusters: int):

@@ -171,3 +171,30 @@ def test_kmeanspp_with_predrawn_numbers_equals_sklearn(n, d, k, seed):
     assert np.random.random_sample() == state_after
     got = O.kmeanspp_predrawn(xc, k, u0, draws)
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ a11: clip + Adam / AdamW
+@pytest.mark.parametrize("decoupled,wd", [(True, 1e-4), (False, 1e-2), (True, 0.0)])
+def test_adam_clip_step_matches_torch_optim(decoupled, wd):
+    """The oracle's restatement of clip_grad_norm_ + torch.optim.AdamW / Adam (the third-party routines behind
+    trainer.py:49-81, :117-118) against torch itself on the CPU, four steps."""
+    import torch
+    rng = np.random.default_rng(0)
+    shapes = [(37, 5), (64,), (1, 1), (300, 7)]
+    p0 = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    tp = [torch.nn.Parameter(torch.from_numpy(x.copy())) for x in p0]
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)(tp, lr=1e-3, weight_decay=wd)
+    p, m, v = [x.copy() for x in p0], [np.zeros_like(x) for x in p0], [np.zeros_like(x) for x in p0]
+    for step in range(1, 5):
+        grads = [(rng.standard_normal(s) * (3.0 if step % 2 else 0.01)).astype(np.float32) for s in shapes]
+        for t, gr in zip(tp, grads):
+            t.grad = torch.from_numpy(gr.copy())
+        want_norm = float(torch.nn.utils.clip_grad_norm_(tp, 1.0))
+        opt.step()
+        p, gc, m, v, norm = O.adam_clip_step(p, grads, m, v, step, 1e-3, weight_decay=wd, decoupled=decoupled, max_norm=1.0)
+        np.testing.assert_allclose(norm, want_norm, rtol=1e-6)
+        for a, t, c in zip(p, tp, gc):
+            np.testing.assert_allclose(c, t.grad.numpy(), rtol=1e-6, atol=0)
+            np.testing.assert_allclose(a, t.detach().numpy(), rtol=1e-5, atol=2e-6)
+        for a, t in zip(m, tp):
+            np.testing.assert_allclose(a, opt.state[t]["exp_avg"].numpy(), rtol=1e-5, atol=1e-8)
