@@ -81,8 +81,12 @@ class DataParallelTrainer(Trainer):
         rq = getattr(self.model, "rq", None)
         if rq is None or not any(not q.initted for q in rq.vq_layers):
             return
+        import inspect
+        kw = {"use_sk": False}                                  # argmin pass: only the k-means side effect is wanted
+        if "use_ema" in inspect.signature(self.model.forward).parameters:
+            kw["use_ema"] = False                               # and no EMA step for the variant of index_improve/
         with torch.no_grad():                                   # same rows, same numpy RNG state on every rank
-            self._model_forward(data.to(self.device))
+            self.model(data.to(self.device), **kw)
 
     def _train_epoch(self, train_data, epoch_idx):
         self.model.train()
