@@ -20,8 +20,13 @@ class StandIn(torch.nn.Module):
         self.dec = torch.nn.Linear(5, 12)
         self.codebook = torch.nn.Parameter(torch.randn(7, 5) * 0.3)
         self.unused = torch.nn.Parameter(torch.zeros(3))           # never receives a gradient
+        self.rq = types.SimpleNamespace(vq_layers=[types.SimpleNamespace(initted=False, sk_epsilon=0.0)])
+        self.init_calls = []                                        # (rows, use_sk) of the k-means initialisation passes
 
-    def forward(self, x):
+    def forward(self, x, use_sk=True):
+        if not self.rq.vq_layers[0].initted:                        # vq.py:67-68: the first batch initialises the codebook
+            self.init_calls.append((x.shape[0], use_sk, torch.is_grad_enabled()))
+            self.rq.vq_layers[0].initted = True
         z = self.enc(x)
         idx = torch.cdist(z.detach(), self.codebook.detach()).argmin(dim=1)
         q = self.codebook[idx]
@@ -53,7 +58,7 @@ def _worker(rank, world, port, tmp, out):
     losses = [tr._train_epoch(_batches(), ep) for ep in range(2)]
     path = tr._save_checkpoint(0, ckpt_file="dp.pth")
     dist.barrier()
-    out[rank] = (losses, [p.detach().clone() for p in model.parameters()], os.path.exists(path))
+    out[rank] = (losses, [p.detach().clone() for p in model.parameters()], os.path.exists(path), model.init_calls)
     dist.destroy_process_group()
 
 
@@ -68,7 +73,8 @@ def test_two_rank_training_equals_single_process(tmp_path):
     tr = Trainer(_args(str(tmp_path)), model, data_num=4)
     ref_losses = [tr._train_epoch(_batches(), ep) for ep in range(2)]
     for rank in (0, 1):
-        losses, params, saved = out[rank]
+        losses, params, saved, init_calls = out[rank]
+        assert init_calls == [(16, False, False)]                  # ONE pass over the full first global batch, argmin, no grad
         np.testing.assert_allclose(np.array(losses), np.array(ref_losses), rtol=2e-5)
         for a, b in zip(params, model.parameters()):
             np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-4, atol=2e-6)
