@@ -244,6 +244,8 @@ class DistributedSinkhorn:
         d = distances_local.detach().to(torch.float64).contiguous()
         b, k = d.shape
         assert k == self.n_codes and d.is_cuda
+        if n_rows_global is None and getattr(self, "n_rows_hint", None) is not None:
+            n_rows_global = int(self.n_rows_hint)       # set by a caller that knows the global batch (no host read)
         if n_rows_global is None:
             t = torch.tensor([b], dtype=torch.int64, device=self.device)
             dist.all_reduce(t, group=self.group)

@@ -42,6 +42,7 @@ class DataParallelTrainer(Trainer):
         super().__init__(args, model, data_num)
         self._flat = None
         self._flat_params = None
+        self._sinkhorn_levels = []
         for p in self.model.parameters():                       # identical replicas whatever the local seed was
             dist.broadcast(p.data, src=dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0,
                            group=self.group)
@@ -53,8 +54,10 @@ class DataParallelTrainer(Trainer):
         from .distributed import DistributedSinkhorn
         rq = getattr(self.model, "rq", None)
         for q in (rq.vq_layers if rq is not None else []):
-            if getattr(q, "sk_epsilon", 0) and q.sk_epsilon > 0 and getattr(q, "dist_sinkhorn", None) is None:
-                q.dist_sinkhorn = DistributedSinkhorn(q.n_e, self.device, self.group)
+            if getattr(q, "sk_epsilon", 0) and q.sk_epsilon > 0:
+                if getattr(q, "dist_sinkhorn", None) is None:
+                    q.dist_sinkhorn = DistributedSinkhorn(q.n_e, self.device, self.group)
+                self._sinkhorn_levels.append(q)
 
     # ---- one all-reduce over every gradient
     def _all_reduce_grads(self):
@@ -99,6 +102,8 @@ class DataParallelTrainer(Trainer):
             plan = ShardPlan(n, self.world)
             local = data[plan.slice(self.rank)].to(self.device)
             weight = local.shape[0] / max(n, 1)
+            for q in self._sinkhorn_levels:
+                q.dist_sinkhorn.n_rows_hint = n                 # the global row count, known here: no all-reduce + host read
             with ops.defer_checks():
                 self.optimizer.zero_grad()
                 self._init_codebooks_on_global_batch(data)
