@@ -253,7 +253,8 @@ def kmeanspp_random_numbers(n_samples, num_clusters):
     import numpy as np
     rs = np.random.mtrand._rand
     trials = 2 + int(np.log(num_clusters))
-    p = np.ones(n_samples, dtype=np.float32).astype(np.float64) / np.float64(np.float32(n_samples))
+    w = np.ones(n_samples, dtype=np.float32)                      # sklearn's unit sample weights, in the data's dtype
+    p = (w / w.sum()).astype(np.float64)                          # RandomState.choice converts p to double
     cdf = p.cumsum()
     cdf /= cdf[-1]
     first = int(cdf.searchsorted(rs.random_sample(), side="right"))
