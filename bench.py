@@ -155,60 +155,119 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_sample_run(ws, bs, cbs, head, n_sample):
-    """The reference algorithm (numpy restatement, literal per-group re-encoding like
-    generate_indices.py:116-119) on a bounded sample; returns (items/s, seconds, stats)."""
-    from oracle import lcrec_oracle as O
-    p = O.RqvaeParams(encoder=O.MlpParams(ws, bs), codebooks=cbs, sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST], sk_iters=SK_ITERS)
-    x = head[:n_sample]
-    t0 = time.perf_counter()
-    codes, trace = O.generate_indices(x, p, batch_size=64, max_rounds=20, reencode=True)
-    dt = time.perf_counter() - t0
-    return n_sample / dt, dt, {"rounds": len(trace.rounds), "collision_rate_pass0": O.collision_rate(trace.codes_pass0),
-                               "collision_rate_final": O.collision_rate(codes)}
+REF_ITEM_RUNS = 150_000      # item-runs the reference arm may spend in total (~4 min at the ~600 items/s of the round-1 box)
+C1_ITEMS = 25_000            # BASELINE.json configs[0]
 
 
-def host_threads():
+def reference_sample_items(steps, warmup):
+    """Items per step of the reference arm: C1 in full (25 000) when steps + warmup <= 6, otherwise the largest sample that
+    keeps the whole `--steps K --warmup W` run within a few minutes.  A pure function of (K, W) so that both arms print it."""
+    return int(min(C1_ITEMS, max(2048, REF_ITEM_RUNS // max(steps + warmup, 1))))
+
+
+def host_cores():
     try:
-        import threadpoolctl
-        info = threadpoolctl.threadpool_info()
-        n = max([i.get("num_threads", 1) for i in info] or [1])
-        return int(n)
+        return len(os.sched_getaffinity(0))
     except Exception:  # noqa: BLE001
         return os.cpu_count() or 1
+
+
+def reference_items(n):
+    from lcrec_b200.synth import synth_items
+    return synth_items(n, DIMS[0], n_parents=max(n // 8, 1), seed=SEED_X)
+
+
+def run_reference_script(ws, bs, cbs, x, device, repeat, threads, timeout_s=1500):
+    """baseline/run_reference.py in a subprocess: the UNMODIFIED index/generate_indices.py (staged under baseline/_ref by
+    build()) on x.  torchrun exports OMP_NUM_THREADS=1; the thread count is set explicitly here.  Returns the runner's dict
+    (seconds per repeat, torch threads, ...) or {"unavailable": why}."""
+    runner = os.path.join(ROOT, "baseline", "run_reference.py")
+    if not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "index", "generate_indices.py")):
+        return {"unavailable": "baseline/_ref/index not staged"}
+    tmp = tempfile.mkdtemp(prefix="lcrec_refarm_")
+    npz = os.path.join(tmp, "in.npz")
+    arrs = {"x": x, "eps": np.array([0.0, 0.0, 0.0, EPS_LAST]), "sk_iters": np.int64(SK_ITERS)}
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        arrs[f"w{i}"] = w; arrs[f"b{i}"] = b
+    for l, cb in enumerate(cbs):
+        arrs[f"cb{l}"] = cb
+    np.savez(npz, **arrs)
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        env[k] = str(threads)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "PYTHONPATH"):
+        env.pop(k, None)
+    out = os.path.join(tmp, "out.json")
+    try:
+        r = subprocess.run([sys.executable, runner, "--npz", npz, "--device", device, "--threads", str(threads), "--repeat", str(repeat),
+                            "--out", out], env=env, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s)
+        if r.returncode != 0 or not os.path.exists(out):
+            return {"unavailable": f"runner exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.load(open(out))
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"runner exceeded {timeout_s} s"}
+    finally:
+        for f in (npz, out):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+
+
+def cpu_port_run(ws, bs, cbs, x):
+    """Fallback when baseline/_ref is not staged: the numpy restatement (oracle), literal per-group re-encoding."""
+    from oracle import lcrec_oracle as O
+    p = O.RqvaeParams(encoder=O.MlpParams(ws, bs), codebooks=cbs, sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST], sk_iters=SK_ITERS)
+    t0 = time.perf_counter()
+    O.generate_indices(x, p, batch_size=64, max_rounds=20, reencode=True)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(ws, bs, cbs, n_items, repeat=1, drop=0):
+    """(dict for the JSON line, mean seconds per run).  kind "reference" = the unmodified script on torch-CPU."""
+    x = reference_items(n_items)
+    cores = host_cores()
+    res = run_reference_script(ws, bs, cbs, x, "cpu", repeat, cores)
+    if "unavailable" not in res:
+        secs = res["seconds"][drop:]
+        dt = float(np.mean(secs))
+        return {"value": n_items / dt, "unit": "items/s", "cores": int(res["torch_threads"]), "kind": "reference", "seconds": dt,
+                "host_cpus": res["cpu_count"], "torch": res["torch"], "rounds": res["rounds"],
+                "collision_rate_final": res["collision_rate_final"],
+                "sample": f"{n_items} items of the same synthetic stream per run: the UNMODIFIED index/generate_indices.py (baseline/_ref, "
+                          f"torch CPU, DataLoader batch 64, per-group re-encoding, JSON dump), {len(secs)} timed run(s)"}, dt
+    secs = [cpu_port_run(ws, bs, cbs, x) for _ in range(repeat)][drop:]
+    dt = float(np.mean(secs))
+    return {"value": n_items / dt, "unit": "items/s", "cores": cores, "kind": "port", "seconds": dt,
+            "sample": f"{n_items} items, numpy restatement of generate_indices.py (oracle; {res['unavailable']})"}, dt
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ws, bs, cbs, head = make_model()
-    n_sample = min(a.cpu_sample or 2048, HEAD_ITEMS)
-    vals = []
-    for i in range(a.warmup + a.steps):
-        v, dt, st = cpu_sample_run(ws, bs, cbs, head, n_sample)
-        if i >= a.warmup:
-            vals.append((v, dt))
-    value = float(np.mean([v for v, _ in vals]))
-    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
-    cores = host_threads()
-    sample = f"{n_sample} items of the same stream (numpy head), full generate_indices incl. per-group re-encoding, per step"
+    ws, bs, cbs, _ = make_model()
+    n_sample = a.cpu_sample or reference_sample_items(a.steps, a.warmup)
+    cpu, dt = cpu_baseline(ws, bs, cbs, n_sample, repeat=a.warmup + a.steps, drop=a.warmup)
+    value = cpu["value"]
     line = {"impl": "reference", "metric": "items indexed/sec (4-level RQ + Sinkhorn collision resolution)", "value": value,
-            "unit": "items/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "unit": "items/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(a.gpus, a.items),
-            "cpu_baseline": {"value": value, "unit": "items/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "collision": st}
+            "config": workload_config(a.gpus, a.items, a.steps, a.warmup, a.cpu_sample),
+            "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
 
 
-def workload_config(gpus, items):
+def workload_config(gpus, items, steps, warmup, cpu_sample=None):
+    n_ref = cpu_sample or reference_sample_items(steps, warmup)
     return {"workload": f"full index generation + collision resolution, {items} synthetic 4096-d items per GPU "
-                        f"(BASELINE.json configs[2]; x{gpus} GPUs = configs[3] shape)",
-            "items_per_gpu": items, "in_dim": DIMS[0], "encoder": DIMS, "levels": len(N_CODES), "codes_per_level": 256,
-            "e_dim": E_DIM, "sk_epsilon_last": EPS_LAST, "sk_iters": SK_ITERS, "max_rounds": 20,
+                        f"(BASELINE.json configs[2]; x{gpus} GPUs = configs[3] shape); the reference arm (--impl reference) runs the "
+                        f"unmodified index/generate_indices.py on a bounded sample of {n_ref} items of the same stream per step "
+                        f"(configs[0] is 25000)",
+            "items_per_gpu": items, "reference_sample_items": n_ref, "in_dim": DIMS[0], "encoder": DIMS, "levels": len(N_CODES),
+            "codes_per_level": 256, "e_dim": E_DIM, "sk_epsilon_last": EPS_LAST, "sk_iters": SK_ITERS, "max_rounds": 20,
             "l2_policy": "inputs (16.4 GB/GPU) larger than L2, no flush", "parallelism": f"items sharded x{gpus}"}
 
 
@@ -352,16 +411,22 @@ def run_gpu_arm(a):
                 "kernel_share_of_step": l1_ms / a.steps / ms_step,
                 "hbm_frac_end_to_end": value / world * BYTES_PER_ITEM / 1e9 / pk["hbm_gbs"], "stage_ms_per_step": stage_ms}
         cpu = None
+        torch_cuda = None
         if world == 1 and not a.no_cpu:
-            n_cpu = min(a.cpu_sample or 8192, HEAD_ITEMS)
-            v, dt, st = cpu_sample_run(ws, bs, cbs, head, n_cpu)
-            cpu = {"value": v, "unit": "items/s", "cores": host_threads(), "kind": "port", "seconds": dt,
-                   "sample": f"{n_cpu} items of the same stream, full generate_indices incl. per-group re-encoding (numpy/OpenBLAS)"}
+            cpu, _ = cpu_baseline(ws, bs, cbs, a.cpu_sample or C1_ITEMS)
+            if not a.no_torch_cuda:
+                # the reference on its own GPU path (torch-CUDA / cuBLAS fp32), same script, same items: the honest GPU comparator
+                res = run_reference_script(ws, bs, cbs, reference_items(a.cpu_sample or C1_ITEMS), f"cuda:{local}", 2, host_cores(), 600)
+                if "unavailable" in res:
+                    torch_cuda = res
+                else:
+                    torch_cuda = {"value": res["items"] / res["seconds"][-1], "unit": "items/s", "items": res["items"], "seconds": res["seconds"][-1],
+                                  "rounds": res["rounds"], "note": "unmodified index/generate_indices.py with device=cuda:0 (second of two runs)"}
         line = {"metric": "items indexed/sec (4-level RQ + Sinkhorn collision resolution)", "value": value, "unit": "items/s",
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (low-rank parents + noise, random-init encoder, k-means-style codebooks)",
-                "config": workload_config(world, n_local), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "stats": stats,
+                "config": workload_config(world, n_local, a.steps, a.warmup, a.cpu_sample), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "stats": stats,
                 "flop_per_item": FLOP_PER_ITEM, "bytes_per_item": BYTES_PER_ITEM,
                 "algorithmic_tflops_end_to_end": value * FLOP_PER_ITEM / 1e12}
         print(json.dumps(line), flush=True)
@@ -381,11 +446,12 @@ def main():
     ap.add_argument("--chunk-rows", dest="chunk_rows", type=int, default=131072)
     ap.add_argument("--e2e-items", dest="e2e_items", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=None,
-                    help="items of the CPU sample: default 8192 for the cpu_baseline leg of the GPU arm (one run, ~15 s on 16 host "
-                         "threads), 2048 per step for --impl reference (warmup + steps runs)")
+                    help="items per run of the unmodified reference script: default 25000 (C1) for the cpu_baseline leg of the GPU arm, "
+                         "reference_sample_items(steps, warmup) per step for --impl reference")
     ap.add_argument("--engine", type=int, default=1, choices=[0, 1], help="GEMM operand encoding: 1 = f16 x3 (default), 0 = tf32 x3")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--no-torch-cuda", dest="no_torch_cuda", action="store_true", help="skip the reference-on-torch-CUDA comparator")
     ap.add_argument("--profile-window", dest="profile_window", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     a = ap.parse_args()

@@ -364,7 +364,9 @@ def kmeanspp_seed(xc: torch.Tensor, n_clusters: int, first_index: int, draws: to
     lib = _lib.load()
     x2 = _f32c(xc)
     n, d = x2.shape
-    dr = draws.detach().to(device=x2.device, dtype=torch.float64).contiguous().reshape(max(n_clusters - 1, 0), -1)
+    dr = draws.detach().to(device=x2.device, dtype=torch.float64).contiguous()
+    if dr.numel():
+        dr = dr.reshape(n_clusters - 1, -1)
     trials = int(dr.shape[1]) if dr.numel() else 1
     idx = torch.empty(n_clusters, dtype=torch.int64, device=x2.device)
     centers = torch.empty((n_clusters, d), dtype=torch.float32, device=x2.device)

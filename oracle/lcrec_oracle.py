@@ -115,11 +115,60 @@ def mlp_forward(x: np.ndarray, p: MlpParams, training_bn: bool = False) -> np.nd
 # --------------------------------------------------------------------------- #
 # a4/a5/a6/a7: one quantiser level
 # --------------------------------------------------------------------------- #
-def vq_distances(latent: np.ndarray, codebook: np.ndarray) -> np.ndarray:
+def fma32(a, b, c):
+    """Correctly rounded fp32 ``fma(a, b, c)`` on arrays: the product of two fp32 numbers is exact in fp64; the fp64 sum
+    ``t`` and its exact error ``e`` (TwoSum) decide the single rounding to fp32, including the double-rounding corner
+    (``t`` exactly half-way between two fp32 numbers while ``e != 0``)."""
+    a64, b64, c64 = (np.asarray(v, F32).astype(F64) for v in (a, b, c))
+    p = a64 * b64
+    t = p + c64
+    r = t.astype(F32)
+    # t is an exact fp32 midpoint iff its low 29 mantissa bits are 1000...0; only then can the second rounding go wrong
+    mid = (np.ascontiguousarray(t).view(np.int64) & 0x1FFFFFFF) == 0x10000000
+    if not mid.any():
+        return r
+    bb = t - p
+    e = (p - (t - bb)) + (c64 - bb)
+    r64 = r.astype(F64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        up = np.nextafter(r, F32(np.inf)).astype(F64)
+        dn = np.nextafter(r, F32(-np.inf)).astype(F64)
+        tie_up = mid & (t > r64) & ((t - r64) == (up - t)) & (e > 0)      # true value beyond the midpoint towards `up`
+        tie_dn = mid & (t < r64) & ((r64 - t) == (t - dn)) & (e < 0)
+    return np.where(tie_up, up.astype(F32), np.where(tie_dn, dn.astype(F32), r))
+
+
+def _chain_dot(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """``out[i, k] = fma(a[i, D-1], b[k, D-1], ... fma(a[i, 0], b[k, 0], 0))``: fp32 sequential chain, d ascending."""
+    acc = np.zeros((a.shape[0], b.shape[0]), dtype=F32)
+    for d in range(a.shape[1]):
+        acc = fma32(a[:, d:d + 1], b[None, :, d], acc)
+    return acc
+
+
+def _chain_sqnorm(a: np.ndarray) -> np.ndarray:
+    acc = np.zeros(a.shape[0], dtype=F32)
+    for d in range(a.shape[1]):
+        acc = fma32(a[:, d], a[:, d], acc)
+    return acc
+
+
+def vq_distances(latent: np.ndarray, codebook: np.ndarray, order: str = "blas") -> np.ndarray:
     """``d = sum(x^2) + sum(c^2)^T - 2 x c^T`` in fp32, evaluation order (xx + cc) - 2 dot
-    (index/models/vq.py:71-73)."""
+    (index/models/vq.py:71-73).
+
+    The reference leaves the fp32 summation ORDER inside ``torch.sum`` / ``torch.matmul`` to the library (MKL on CPU,
+    cuBLAS on CUDA; it changes with the batch shape and the thread count), so distances are defined up to a few ulp.
+    ``order="blas"``: numpy pairwise sums + OpenBLAS sgemm (one such library order).
+    ``order="chain"``: every sum as one fp32 fma chain in ascending dimension - the order the CUDA kernels use
+    (``csrc/rq_fused.cu``, ``csrc/sinkhorn.cu``); with it the oracle is comparable bit for bit with the device path."""
     latent = latent.astype(F32, copy=False)
     codebook = codebook.astype(F32, copy=False)
+    if order == "chain":
+        xx = _chain_sqnorm(latent)[:, None]
+        cc = _chain_sqnorm(codebook)[None, :]
+        dot = _chain_dot(latent, codebook)
+        return ((xx + cc).astype(F32) - F32(2) * dot).astype(F32)
     xx = np.sum(latent * latent, axis=1, keepdims=True, dtype=F32)
     cc = np.sum(codebook * codebook, axis=1, keepdims=True, dtype=F32).T
     dot = latent @ codebook.T
@@ -170,9 +219,9 @@ def _argmax_first_nan_wins(q: np.ndarray) -> np.ndarray:
 
 
 def vq_assign(latent: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: float,
-              sk_iters: int, want_q: bool = False):
+              sk_iters: int, want_q: bool = False, order: str = "blas"):
     """Index selection of ``VectorQuantizer.forward`` (index/models/vq.py:71-83)."""
-    d = vq_distances(latent, codebook)
+    d = vq_distances(latent, codebook, order)
     if (not use_sk) or sk_epsilon <= 0:
         idx = np.argmin(d, axis=-1).astype(np.int64)   # first minimum, like torch.argmin
         return (idx, d, None) if want_q else idx
@@ -526,6 +575,98 @@ def generate_indices(x: np.ndarray, p: RqvaeParams, batch_size: int = 64, max_ro
         trace.n_rows.append(rows)
         tt += 1
     return codes, trace
+
+
+def resolve_collisions(codes_pass0: np.ndarray, resid_last: np.ndarray, codebook_last: np.ndarray,
+                       sk_epsilon: float, sk_iters: int, max_rounds: int = 20, order: str = "blas") -> Tuple[np.ndarray, GenTrace]:
+    """The collision rounds of ``index/generate_indices.py:107-128`` started from GIVEN inputs of the last
+    level: the PASS-0 table and the residual entering the last quantiser (``rq.py:45-48``).
+
+    Every group is an independent Sinkhorn problem on its own rows (``vq.py:71-83``).  With the latents
+    held fixed, levels 0..L-2 of a re-quantised row are its PASS-0 argmin codes again (their epsilon is
+    forced to 0, ``generate_indices.py:101-103``), so only the last column changes.  This is the form the
+    parity tests use to separate the LOOP (integer bookkeeping + fp64 Sinkhorn: must be bit-exact on
+    equal inputs) from the ENCODER (fp32 GEMMs: equal within 1e-5 relative, never bitwise - the reference
+    itself re-encodes every group at a different batch shape).
+    """
+    codes = np.array(codes_pass0, dtype=np.int64, copy=True)
+    n = codes.shape[0]
+    trace = GenTrace(codes_pass0=codes.copy())
+    tt = 0
+    while tt < max_rounds and n_unique_codes(codes) != n:
+        groups = collision_groups(codes)
+        rows = 0
+        for g in groups:
+            codes[g, -1] = vq_assign(resid_last[g], codebook_last, True, sk_epsilon, sk_iters, order=order)
+            rows += len(g)
+        trace.rounds.append(codes.copy())
+        trace.n_groups.append(len(groups))
+        trace.n_rows.append(rows)
+        tt += 1
+    return codes, trace
+
+
+@dataclass
+class LoopLedger:
+    """Per-row account of how two runs of the collision loop differ."""
+    rows_differing_final: int = 0
+    first_round: int = -1                      # first round (1-based) after which any row differs
+    primary: List[Tuple[int, int]] = field(default_factory=list)   # (round, item): same group + same incoming table, other pick
+    cascade: int = 0                           # rows whose first difference comes from a group that already differed
+    per_round: List[int] = field(default_factory=list)
+
+
+def loop_ledger(tables_a: Sequence[np.ndarray], tables_b: Sequence[np.ndarray]) -> LoopLedger:
+    """Compare two per-round table sequences ``[pass0, after round 1, ...]`` of the same items.
+
+    A row's FIRST difference (round r) is *primary* when the group that re-quantised it in round r had
+    the same members and the same incoming codes in both runs - the two sides then solved the same
+    Sinkhorn problem on (nominally) the same rows and picked differently, which only input rounding or a
+    kernel defect can cause; it is a *cascade* when the group itself already differed (a consequence of an
+    earlier primary difference).  Shorter sequences are padded with their last table (a run that stopped).
+    """
+    ta, tb = list(tables_a), list(tables_b)
+    m = max(len(ta), len(tb))
+    ta += [ta[-1]] * (m - len(ta)); tb += [tb[-1]] * (m - len(tb))
+    led = LoopLedger()
+    n = ta[0].shape[0]
+    seen = np.zeros(n, dtype=bool) | (ta[0] != tb[0]).any(axis=1)
+    led.per_round.append(int(seen.sum()))
+    for r in range(1, m):
+        diff = (ta[r] != tb[r]).any(axis=1)
+        led.per_round.append(int(diff.sum()))
+        new = np.nonzero(diff & ~seen)[0]
+        if len(new) and led.first_round < 0:
+            led.first_round = r
+        if len(new):
+            ga = {g[0]: g for g in collision_groups(ta[r - 1])}
+            gb = {g[0]: g for g in collision_groups(tb[r - 1])}
+            owner_a = {}
+            for g in ga.values():
+                for i in g:
+                    owner_a[i] = g
+            for i in new:
+                g = owner_a.get(int(i))
+                same = g is not None and gb.get(g[0]) == g and bool((ta[r - 1][g] == tb[r - 1][g]).all())
+                if same:
+                    led.primary.append((r, int(i)))
+                else:
+                    led.cascade += 1
+        seen |= diff
+    led.rows_differing_final = int((ta[-1] != tb[-1]).any(axis=1).sum())
+    return led
+
+
+def distance_ulp_witness(resid_a: np.ndarray, resid_b: np.ndarray, codebook: np.ndarray, order_a: str = "blas",
+                         order_b: str = "blas") -> Tuple[float, float]:
+    """For one group solved on two roundings of the same rows: (max difference of the fp32 distance matrices
+    ``vq.py:71-73`` in ulps of the entry, max relative difference of the residual rows).  The pair is the
+    constructive witness "the other pick follows from an N-ulp perturbation of the distances"."""
+    da, db = vq_distances(resid_a, codebook, order_a), vq_distances(resid_b, codebook, order_b)
+    ulp = np.spacing(np.maximum(np.abs(da), np.abs(db)).astype(F32)).astype(F64)
+    n_ulp = float(np.max(np.abs(da.astype(F64) - db.astype(F64)) / ulp))
+    scale = max(float(np.abs(resid_a).max()), 1e-30)
+    return n_ulp, float(np.abs(resid_a.astype(F64) - resid_b.astype(F64)).max() / scale)
 
 
 def codes_to_tokens(codes: np.ndarray) -> List[List[str]]:

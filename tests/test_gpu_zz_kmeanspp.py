@@ -1,11 +1,7 @@
-"""NOT collected by default (file name): the device k-means++ seeding (lcrec_kmeanspp_seed, LCREC_KMEANS=device_seed) was
-written after the round's GPU budget was spent and has not run on hardware yet.  First thing to run in round 2:
-
-    python -m pytest tests/pending_gpu/kmeanspp_seed_check.py -q -m gpu
-
-Expected: the seeds equal scikit-learn's `kmeans_plusplus` with the same numpy seed (the CPU restatement
-oracle.kmeanspp_predrawn and a numpy emulation of the kernel's summation orders both reproduce them exactly on these shapes),
-and the whole `kmeans()` call then agrees with `KMeans(n_clusters, max_iter).fit` like the "device" backend does."""
+"""Device k-means++ seeding (lcrec_kmeanspp_seed, LCREC_KMEANS=device_seed; SURVEY 8(f) rank 1, reference layers.py:69-82):
+the seeds equal scikit-learn's `kmeans_plusplus` with the same numpy seed, and the whole `kmeans()` call then agrees with
+`KMeans(n_clusters, max_iter).fit` like the "device" backend does.  First run on a B200 in round 2 (3 of 4 shapes passed at
+once; the n_clusters = 1 case needed a host-side fix for the empty draw matrix)."""
 import numpy as np
 import pytest
 import torch
