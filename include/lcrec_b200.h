@@ -164,8 +164,9 @@ int lcrec_sinkhorn_dense(const double* distances, int64_t n_rows, int n_codes, d
  * of a data-parallel job (the DP form of the training step, trainer.py:114): row steps are local, the initial total
  * and the per-iteration column marginals are summed inside the kernel through peer memory (NVLink P2P on symmetric
  * buffers, rank-ordered sum => identical marginals on all ranks).  peers_dev: device array of `world` pointers to the
- * ranks' symmetric buffers (lcrec_sinkhorn_dist_symmetric_bytes each, zeroed once); epoch must grow by >= iters + 2
- * per call.  Collective: every rank calls it with its own rows.  Workspace as lcrec_sinkhorn_workspace_bytes. */
+ * ranks' symmetric buffers (lcrec_sinkhorn_dist_symmetric_bytes each, zeroed once); epoch = steps published on these
+ * buffers so far: 0 for the first call, then EXACTLY the previous call's epoch + its iters + 1 (the double-buffered slots
+ * alternate on the absolute step, so consecutive calls may overlap without a barrier in between).  Collective: every rank calls it with its own rows.  Workspace as lcrec_sinkhorn_workspace_bytes. */
 int64_t lcrec_sinkhorn_dist_symmetric_bytes(int n_codes);
 int lcrec_sinkhorn_dense_dist(const double* distances, int64_t n_rows_local, int64_t n_rows_global, int n_codes,
                               double epsilon, int iters, double* q, int64_t* argmax, int32_t* flags,

@@ -42,7 +42,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    tmp = LIB + ".tmp"       # link aside, then rename: a snapshot taken meanwhile never sees a half-written library
+    subprocess.check_call([nvcc, "-shared", "-o", tmp, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -255,7 +255,7 @@ class DistributedSinkhorn:
         flags = torch.zeros(1, dtype=torch.int32, device=self.device)
         ws = _ws(self.lib.lcrec_sinkhorn_workspace_bytes(max(b, 1), k), self.device)
         epoch = self.epoch
-        self.epoch += int(iters) + 2
+        self.epoch += int(iters) + 1            # exactly the steps this call publishes: slots alternate across calls
         with torch.cuda.device(self.device):
             _lib.check(self.lib.lcrec_sinkhorn_dense_dist(_p(d), b, int(n_rows_global), k, float(epsilon), int(iters), _p(q), _p(arg),
                                                           _p(flags), _p(self.peers), self.world, self.rank, C.c_uint64(epoch),

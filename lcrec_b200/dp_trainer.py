@@ -14,7 +14,9 @@ things cross NVLink, as the north star asks:
   (``lcrec_adam_clip_step``), so the replicas never diverge.
 
 Codebook k-means initialisation (first batch, ``vq.py:67-68``) runs on the full global batch on every rank with the same
-numpy seed.  BatchNorm in training mode would need synchronised batch statistics and is refused.  Rank 0 writes checkpoints.
+numpy seed, after which rank 0's codebooks are broadcast.  BatchNorm in training mode would need synchronised batch
+statistics and is refused, and so is the EMA-codebook variant of index_improve/ (its in-place per-rank updates would make the
+replicas diverge).  A rank whose row block is empty still joins the Sinkhorn collectives.  Rank 0 writes checkpoints.
 """
 from __future__ import annotations
 
@@ -39,6 +41,12 @@ class DataParallelTrainer(Trainer):
         if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in model.modules()):
             raise NotImplementedError("data-parallel training with BatchNorm needs synchronised batch statistics "
                                       "(the single-device global-batch semantics of the reference); use bn=False")
+        if any(name.endswith("_ema_cluster_size") for name, _ in model.named_buffers()):
+            # index_improve's EMA codebooks are updated in place from the rows a rank sees (lcrec_ema_update): with sharded
+            # rows the replicas' counts, sums and codebooks would drift apart from step 1, and the dead-code reset draws
+            # from the local RNG and local latents.  Refused like BatchNorm until the counts and sums are all-reduced.
+            raise NotImplementedError("data-parallel training of the EMA-codebook variant (index_improve) needs the per-code "
+                                      "counts and sums reduced over the ranks before smoothing; train it on one device")
         super().__init__(args, model, data_num)
         self._flat = None
         self._flat_params = None
@@ -81,15 +89,37 @@ class DataParallelTrainer(Trainer):
             p.grad = v
 
     def _init_codebooks_on_global_batch(self, data):
+        """First training batch (vq.py:67-68): every level's k-means runs on the FULL global batch, on every rank, with the
+        caller's `use_sk` - in the reference's single-device step the residual that feeds level l + 1's k-means comes from
+        level l's Sinkhorn assignment whenever that level has sk_epsilon > 0.  Every rank holds all the rows here, so the
+        Sinkhorn levels use the local dense kernel for this one pass.  Afterwards the codebooks are broadcast from rank 0:
+        replica equality must not rest on every rank's numpy RNG being in the same state."""
         rq = getattr(self.model, "rq", None)
         if rq is None or not any(not q.initted for q in rq.vq_layers):
             return
-        import inspect
-        kw = {"use_sk": False}                                  # argmin pass: only the k-means side effect is wanted
-        if "use_ema" in inspect.signature(self.model.forward).parameters:
-            kw["use_ema"] = False                               # and no EMA step for the variant of index_improve/
-        with torch.no_grad():                                   # same rows, same numpy RNG state on every rank
-            self.model(data.to(self.device), **kw)
+        saved = [(q, q.dist_sinkhorn) for q in rq.vq_layers if getattr(q, "dist_sinkhorn", None) is not None]
+        for q, _ in saved:
+            q.dist_sinkhorn = None
+        try:
+            with torch.no_grad():
+                self.model(data.to(self.device))
+        finally:
+            for q, ds in saved:
+                q.dist_sinkhorn = ds
+        src = dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0
+        for q in rq.vq_layers:
+            if hasattr(q, "embedding"):
+                dist.broadcast(q.embedding.weight.data, src=src, group=self.group)
+
+    def _join_forward_collectives(self):
+        """A rank whose row block of this batch is empty still has to take part in the collectives of the forward pass: per
+        Sinkhorn level the 2-element MAX all-reduce of the centring and the in-kernel arrival of the marginal all-reduce
+        (both accept 0 local rows).  Skipping them would leave the peers' collectives mismatched with this rank's next one."""
+        for q in self._sinkhorn_levels:
+            d = torch.empty((0, q.n_e), dtype=torch.float32, device=self.device)
+            dc = q.dist_sinkhorn.center(d)
+            _, _, flags = q.dist_sinkhorn(dc, q.sk_epsilon, q.sk_iters)
+            ops.check_later("sinkhorn", flags)
 
     def _train_epoch(self, train_data, epoch_idx):
         self.model.train()
@@ -113,6 +143,8 @@ class DataParallelTrainer(Trainer):
                     loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=local)
                     (loss * weight).backward()
                     stats = torch.stack([loss.detach(), loss_recon.detach()]).float() * weight
+                else:
+                    self._join_forward_collectives()
                 self._all_reduce_grads()
                 dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)     # the global-batch loss values
                 self._check_nan(stats[0])

@@ -131,8 +131,11 @@ class MLPLayers(nn.Module):
         blocks.append(cur)
         return blocks
 
-    def _fused_ok(self) -> bool:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+    def _fused_ok(self, input_feature=None) -> bool:
+        """The no-autograd handle path serves the call only when nothing needs a gradient: neither a parameter nor the
+        INPUT (a frozen stack in front of a trainable one must still propagate d/dx like nn.Sequential would)."""
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or (input_feature is not None and input_feature.requires_grad)):
             return False
         blocks = self._blocks()
         for i, (dp, lin, bn, act) in enumerate(blocks):
@@ -189,7 +192,7 @@ class MLPLayers(nn.Module):
     def forward(self, input_feature):
         if not input_feature.is_cuda:
             raise RuntimeError("lcrec_b200.MLPLayers runs on CUDA only (no CPU fallback)")
-        if self._fused_ok():
+        if self._fused_ok(input_feature):
             return self._get_handle().forward(input_feature)
         if self._stack_ok():
             handle = self._get_handle()

@@ -74,7 +74,7 @@ def test_two_rank_training_equals_single_process(tmp_path):
     ref_losses = [tr._train_epoch(_batches(), ep) for ep in range(2)]
     for rank in (0, 1):
         losses, params, saved, init_calls = out[rank]
-        assert init_calls == [(16, False, False)]                  # ONE pass over the full first global batch, argmin, no grad
+        assert init_calls == [(16, True, False)]                   # ONE pass over the full first global batch, the step's use_sk, no grad
         np.testing.assert_allclose(np.array(losses), np.array(ref_losses), rtol=2e-5)
         for a, b in zip(params, model.parameters()):
             np.testing.assert_allclose(a.numpy(), b.detach().numpy(), rtol=2e-4, atol=2e-6)
