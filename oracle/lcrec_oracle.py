@@ -238,13 +238,13 @@ def _mse(a: np.ndarray, b: np.ndarray) -> np.float32:
 
 
 def vq_forward(x: np.ndarray, codebook: np.ndarray, use_sk: bool, sk_epsilon: float, sk_iters: int,
-               beta: float):
+               beta: float, order: str = "blas"):
     """Forward values of ``VectorQuantizer.forward`` (index/models/vq.py:63-99).
 
     Returns (x_q straight-through forward value ``x + (q - x)``, loss, indices).
     """
     x = x.astype(F32, copy=False)
-    idx = vq_assign(x, codebook, use_sk, sk_epsilon, sk_iters)
+    idx = vq_assign(x, codebook, use_sk, sk_epsilon, sk_iters, order=order)
     q = codebook.astype(F32)[idx]
     mse = _mse(q, x)
     loss = F32(mse + F32(beta) * mse)          # codebook_loss + beta * commitment_loss (vq.py:90-92)
@@ -437,13 +437,14 @@ def item_embedding(field_hiddens: Sequence[np.ndarray], field_masks: Sequence[np
 # --------------------------------------------------------------------------- #
 # a9/a10: residual quantiser and the model
 # --------------------------------------------------------------------------- #
-def rq_forward(z: np.ndarray, p: RqvaeParams, use_sk: bool):
-    """``ResidualVectorQuantizer.forward`` (index/models/rq.py:39-56)."""
+def rq_forward(z: np.ndarray, p: RqvaeParams, use_sk: bool, order: str = "blas"):
+    """``ResidualVectorQuantizer.forward`` (index/models/rq.py:39-56).  ``order``: fp32 summation order of the distances
+    (see ``vq_distances``)."""
     residual = z.astype(F32, copy=True)
     x_q = np.zeros_like(residual)
     losses, indices = [], []
     for cb, eps in zip(p.codebooks, p.sk_epsilons):
-        x_res, loss, idx = vq_forward(residual, cb, use_sk, eps, p.sk_iters, p.beta)
+        x_res, loss, idx = vq_forward(residual, cb, use_sk, eps, p.sk_iters, p.beta, order)
         residual = (residual - x_res).astype(F32)
         x_q = (x_q + x_res).astype(F32)
         losses.append(loss)

@@ -438,11 +438,30 @@ def test_model_matches_reference(golden, name):
         xq, loss, idx = m.rq(T(g["latents"]), use_sk=False)               # teacher-forced on reference latents
         np.testing.assert_allclose(xq.cpu().numpy(), g["rq_xq"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(loss.item(), g["rq_loss"], rtol=1e-5)
-        out, rq_loss, fidx = m(x[:512], use_sk=True)
+        # use_sk=True (the training forward, vq.py:76-83: one dense Sinkhorn problem on the last level).  Teacher-forced on
+        # the REFERENCE latents of those rows: the residual quantiser must equal the oracle evaluated in the kernels' fp32
+        # summation order exactly (codes) / within 1e-5 (x_q, loss); against the reference's own indices (torch / MKL
+        # summation order, encoder re-run at batch 512) the differing rows are COUNTED: at most 2 of 512, each one a row whose
+        # pick the oracle reproduces on the same latents.
+        lat = g["latents"][:512]
+        xq_s, loss_s, idx_s = m.rq(T(lat), use_sk=True)
+        oxq, oloss, oidx = O.rq_forward(lat, p, use_sk=True, order="chain")
+        assert (idx_s.cpu().numpy() == oidx).all()
+        np.testing.assert_allclose(xq_s.cpu().numpy(), oxq, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(loss_s.item(), float(oloss), rtol=1e-5)
+        counted_tf = int((oidx != g["fwd_idx"]).any(axis=1).sum())
+        assert counted_tf <= 2, counted_tf
+        if counted_tf == 0:
+            np.testing.assert_allclose(loss_s.item(), g["fwd_rq_loss"], rtol=1e-5)
+        out, rq_loss, fidx = m(x[:512], use_sk=True)                       # the whole forward from the embeddings
         tot, rec = m.compute_loss(out, rq_loss, xs=x[:512])
-    assert (fidx.cpu().numpy() != g["fwd_idx"]).any(axis=1).mean() < 0.01
-    np.testing.assert_allclose(rec.item(), g["fwd_recon"], rtol=1e-4)
-    np.testing.assert_allclose(tot.item(), g["fwd_total"], rtol=1e-4)
+    counted = int((fidx.cpu().numpy() != g["fwd_idx"]).any(axis=1).sum())
+    print(f"\n[{name}] use_sk forward: rows differing from the reference: teacher-forced on its latents {counted_tf}/512, "
+          f"from the embeddings {counted}/512")
+    assert counted <= 2, counted
+    tol = 1e-5 if counted == 0 else 1e-4          # a differing row moves a mean over 512 rows by up to ~1/512 of its term
+    np.testing.assert_allclose(rec.item(), g["fwd_recon"], rtol=tol)
+    np.testing.assert_allclose(tot.item(), g["fwd_total"], rtol=tol)
     # VectorQuantizer.get_code alias
     vq = m.rq.vq_layers[0]
     assert torch.equal(vq.get_code(z, use_sk=False), T(codes[:, 0]))
@@ -459,7 +478,10 @@ def test_generate_indices_rounds_teacher_forced(golden, name):
     pass0 = ix.codes_view(n).cpu().numpy().copy()
     assert (pass0 != g["codes_pass0"]).any(axis=1).sum() <= 2
     tables = [g["codes_pass0"]] + list(g["rounds"])
-    bad = rows = 0
+    resid = ix.resid_view(n).cpu().numpy().copy()
+    cb_last = p.codebooks[-1]
+    eps = O.generation_epsilons(p)[-1]
+    counted = hard = rows = 0
     for t in range(len(tables) - 1):
         ix.codes_view(n).copy_(T(tables[t]))
         c = ix.round(n)
@@ -467,9 +489,20 @@ def test_generate_indices_rounds_teacher_forced(golden, name):
         assert c["n_groups"] == len(grp) and c["n_rows"] == sum(len(v) for v in grp)
         assert c["n_unique"] == O.n_unique_codes(tables[t])
         got = ix.codes_view(n).cpu().numpy()
-        bad += int((got != tables[t + 1]).any(axis=1).sum()); rows += c["n_rows"]
-    # exact apart from GEMM-rounding near-ties in the centred distances
-    assert bad <= max(2, rows // 500), (bad, rows)
+        rows += c["n_rows"]
+        bad = np.nonzero(got[:, -1] != tables[t + 1][:, -1])[0]
+        owner = {i: gi for gi, gg in enumerate(grp) for i in gg}
+        for gi in sorted({owner[int(i)] for i in bad}):
+            gg = grp[gi]
+            # counted = the kernels are exact on their own rows (oracle in the kernels' summation order makes the same pick);
+            # the difference to the reference then comes from the fp32 rounding of the rows (encoder GEMMs, 1e-5 bar)
+            exact = bool((O.vq_assign(resid[gg], cb_last, True, eps, p.sk_iters, order="chain") == got[gg, -1]).all())
+            k = int(np.isin(bad, gg).sum())
+            counted += k if exact else 0
+            hard += 0 if exact else k
+    print(f"\n[{name}] teacher-forced rounds: {rows} Sinkhorn rows, counted {counted}, hard {hard}")
+    assert hard == 0
+    assert counted <= max(2, rows // 500), (counted, rows)
 
 
 @pytest.mark.parametrize("name", ["small_model", "bn_model"])
@@ -483,7 +516,17 @@ def test_generate_indices_end_to_end(golden, name, tmp_path):
     assert stats_dev["n_unique"] == O.n_unique_codes(codes_dev.numpy())
     assert stats_dev["max_multiplicity"] == O.max_conflicts(codes_dev.numpy())
     assert abs(stats_dev["collision_rate"] - O.collision_rate(ref_final)) < 5e-3
-    assert (codes_dev.numpy() != ref_final).any(axis=1).mean() < 0.05
+    # LOOP exact on its own inputs (oracle from the GPU's PASS-0 table + residual rows, kernel summation order) ...
+    ix = G.build_indexer(m, n)
+    ix.pass0(T(g["x"]))
+    c0, r3 = ix.codes_view(n).cpu().numpy().copy(), ix.resid_view(n).cpu().numpy().copy()
+    want, tr = O.resolve_collisions(c0, r3, p.codebooks[-1], O.generation_epsilons(p)[-1], p.sk_iters, order="chain")
+    assert (codes_dev.numpy() == want).all()
+    # ... and against the reference's own run a ledger: primary rows (same group, same incoming table, other pick) + cascades
+    led = O.loop_ledger([g["codes_pass0"]] + list(g["rounds"]), [c0] + tr.rounds)
+    print(f"\n[{name}] end to end vs the reference script: {led.rows_differing_final}/{n} rows differ = {len(led.primary)} primary "
+          f"(+ PASS-0 near-ties {led.per_round[0]}) and {led.cascade} cascade rows; per round {led.per_round}")
+    assert led.rows_differing_final <= max(4, n // 100) and len(led.primary) <= 6
     assert (codes_dev.numpy()[:, :3] != ref_final[:, :3]).any(axis=1).sum() <= 2
     G.write_index_json(codes_dev, str(tmp_path / "a.json"))
     assert (tmp_path / "a.json").read_text() == O.index_json(codes_dev.numpy())
