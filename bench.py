@@ -42,6 +42,22 @@ BYTES_PER_ITEM = DIMS[0] * 4 + len(N_CODES) * 8                       # 16 416 B
 FLOP_PER_ITEM = 2 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:])) + len(N_CODES) * 2 * 256 * E_DIM   # 22 433 792
 
 
+def set_config(name):
+    """c3 (default; BASELINE configs[2] / [3]): 4 x 256 codes, e_dim 32.  c5 (configs[4]): 4 x 8192 codes, e_dim 256 (encoder tail
+    64 -> 256; tensor-core distance GEMM path).  c2 (configs[1]) is the training epoch: run_c2()."""
+    global DIMS, N_CODES, E_DIM, BYTES_PER_ITEM, FLOP_PER_ITEM, CONFIG
+    CONFIG = name
+    if name == "c5":
+        DIMS = [4096, 2048, 1024, 512, 256, 128, 64, 256]
+        N_CODES = [8192] * 4
+        E_DIM = 256
+    BYTES_PER_ITEM = DIMS[0] * 4 + len(N_CODES) * 8
+    FLOP_PER_ITEM = 2 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:])) + sum(2 * k * E_DIM for k in N_CODES)
+
+
+CONFIG = "c3"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -72,6 +88,12 @@ def make_model():
     resid = z.copy()
     cbs = []
     for k in N_CODES:
+        if k * 4 > resid.shape[0]:          # large codebooks (c5): residual rows + a little noise, no Lloyd steps
+            cb = resid[rng.integers(0, resid.shape[0], size=k)] + np.float32(1e-3 * resid.std()) * rng.standard_normal((k, resid.shape[1]), dtype=np.float32)
+            d = (resid ** 2).sum(1, keepdims=True) + (cb ** 2).sum(1)[None] - 2 * resid @ cb.T
+            resid = resid - cb[d.argmin(1)]
+            cbs.append(cb.astype(np.float32))
+            continue
         cb = resid[rng.choice(resid.shape[0], k, replace=False)].copy()
         for _ in range(4):
             d = (resid ** 2).sum(1, keepdims=True) + (cb ** 2).sum(1)[None] - 2 * resid @ cb.T
@@ -262,12 +284,13 @@ def run_reference_arm(a):
 
 def workload_config(gpus, items, steps, warmup, cpu_sample=None):
     n_ref = cpu_sample or reference_sample_items(steps, warmup)
+    which = "BASELINE.json configs[4] shape: 4 x 8192 codes, e_dim 256" if CONFIG == "c5" else "BASELINE.json configs[2]"
     return {"workload": f"full index generation + collision resolution, {items} synthetic 4096-d items per GPU "
-                        f"(BASELINE.json configs[2]; x{gpus} GPUs = configs[3] shape); the reference arm (--impl reference) runs the "
+                        f"({which}; x{gpus} GPUs = configs[3] shape); the reference arm (--impl reference) runs the "
                         f"unmodified index/generate_indices.py on a bounded sample of {n_ref} items of the same stream per step "
                         f"(configs[0] is 25000)",
             "items_per_gpu": items, "reference_sample_items": n_ref, "in_dim": DIMS[0], "encoder": DIMS, "levels": len(N_CODES),
-            "codes_per_level": 256, "e_dim": E_DIM, "sk_epsilon_last": EPS_LAST, "sk_iters": SK_ITERS, "max_rounds": 20,
+            "codes_per_level": N_CODES[0], "e_dim": E_DIM, "sk_epsilon_last": EPS_LAST, "sk_iters": SK_ITERS, "max_rounds": 20,
             "l2_policy": "inputs (16.4 GB/GPU) larger than L2, no flush", "parallelism": f"items sharded x{gpus}"}
 
 
@@ -381,6 +404,35 @@ def run_gpu_arm(a):
                "note": "lcrec_indexer_run_host: pinned host embeddings -> codes in host memory; each rank indexes its own items"}
         del xh
 
+    # ---- multi-GPU correctness, untimed: the sharded path over a union of subsets == ONE GPU over the same union (bit for bit)
+    sharded_ok = None
+    if world > 1:
+        n_sub = min(n_local, max(1024, a.check_items // world))
+        sub_plan = ShardPlan(n_sub * world, world)
+        c_sh, _ = generate_codes_sharded(backend, x[:n_sub], sub_plan, rank, 20)
+        all_codes = torch.empty((n_sub * world, c_sh.shape[1]), dtype=c_sh.dtype, device=device)
+        dist.all_gather_into_tensor(all_codes, c_sh.contiguous())
+        all_x = torch.empty((n_sub * world, DIMS[0]), dtype=torch.float32, device=device) if rank == 0 else None
+        dist.gather(x[:n_sub].contiguous(), list(all_x.split(n_sub)) if rank == 0 else None, dst=0)
+        flag = torch.zeros(1, dtype=torch.int64, device=device)
+        if rank == 0:
+            c_one, _ = ix.run_device(all_x, 20)
+            flag[0] = int(torch.equal(c_one, all_codes))
+            del all_x
+        dist.broadcast(flag, src=0)
+        sharded_ok = {"equal": bool(flag.item()), "items": n_sub * world,
+                      "note": "generate_codes_sharded over the ranks' first items vs lcrec_indexer_run_device on rank 0 over their union"}
+    # ---- `.index.json` emission of this rank's table (generate_indices.py:138-145), outside the timed region like in the script
+    json_ms = None
+    if rank == 0:
+        cdev = codes.to(device) if not codes.is_cuda else codes
+        ops.index_json_bytes(cdev[:1024])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        blob = ops.index_json_bytes(cdev)
+        json_ms = {"device_emitter_ms": (time.perf_counter() - t0) * 1e3, "bytes": len(blob), "rows": int(cdev.shape[0]),
+                   "note": "lcrec_index_json + one D2H of the text; the reference's Python dict + json.dump is ~2 us/row"}
+        del blob
     if rank == 0:
         # roofline of the dominant kernel: encoder layer 1 (4096 -> 2048)
         l1_ms, l1_calls = prof.get(1, (0.0, 0))
@@ -426,7 +478,7 @@ def run_gpu_arm(a):
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (low-rank parents + noise, random-init encoder, k-means-style codebooks)",
                 "config": workload_config(world, n_local, a.steps, a.warmup, a.cpu_sample), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "stats": stats,
+                "roofline": roof, "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "index_json": json_ms, "sharded_equals_single": sharded_ok, "stats": stats,
                 "flop_per_item": FLOP_PER_ITEM, "bytes_per_item": BYTES_PER_ITEM,
                 "algorithmic_tflops_end_to_end": value * FLOP_PER_ITEM / 1e12}
         print(json.dumps(line), flush=True)
@@ -434,6 +486,198 @@ def run_gpu_arm(a):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# ----------------------------------------------------------------------------- c2: the training epoch (BASELINE configs[1])
+C2_ITEMS, C2_BATCH = 25_000, 1024
+C2_FLOP_PER_ITEM = 3 * 2 * 2 * sum(a * b for a, b in zip(DIMS[:-1], DIMS[1:])) + 4 * 2 * 256 * 32      # fwd + dgrad + wgrad, encoder + decoder
+
+
+def c2_reference_batches(steps, warmup):
+    return int(min(25, max(2, 100 // max(steps + warmup, 1))))
+
+
+def c2_weights():
+    from lcrec_b200.synth import seeded_weights
+    ws, bs, cbs = seeded_weights(DIMS, N_CODES, E_DIM, seed=SEED_W, cb_scale=0.3)
+    wd, bd, _ = seeded_weights(DIMS[::-1], N_CODES, E_DIM, seed=SEED_W + 1)
+    return ws, bs, wd, bd, cbs
+
+
+def c2_config(gpus, steps, warmup, bn):
+    nb = c2_reference_batches(steps, warmup)
+    return {"workload": f"RQ-VAE training epoch (BASELINE.json configs[1], index/main.py + run.sh shape): {C2_ITEMS} synthetic 4096-d items, "
+                        f"batch {C2_BATCH} (24 full batches + one of 424), AdamW lr 1e-3 wd 1e-4, linear warm-up, clip 1.0, Sinkhorn "
+                        f"(eps 0.003, 50 it) on level 4, bn={bn}; a step = one epoch; the reference arm times the unmodified "
+                        f"Trainer._train_epoch on {nb} batches per step",
+            "items": C2_ITEMS, "batch": C2_BATCH, "bn": bn, "encoder": DIMS, "levels": 4, "codes_per_level": 256, "e_dim": E_DIM,
+            "reference_sample_batches": nb, "l2_policy": "22 M parameters + Adam state (358 MB) and the batch stream exceed L2; no flush",
+            "parallelism": f"data parallel x{gpus}" if gpus > 1 else "single GPU"}
+
+
+def run_reference_train(ws, bs, wd, bd, cbs, x, device, repeat, threads, bn, timeout_s=1500):
+    runner = os.path.join(ROOT, "baseline", "run_reference_train.py")
+    if not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "index", "trainer.py")):
+        return {"unavailable": "baseline/_ref/index not staged"}
+    tmp = tempfile.mkdtemp(prefix="lcrec_reftrain_")
+    npz, out = os.path.join(tmp, "in.npz"), os.path.join(tmp, "out.json")
+    arrs = {"x": x}
+    for i, (w, b, w2, b2) in enumerate(zip(ws, bs, wd, bd)):
+        arrs[f"w{i}"] = w; arrs[f"b{i}"] = b; arrs[f"wd{i}"] = w2; arrs[f"bd{i}"] = b2
+    for l, cb in enumerate(cbs):
+        arrs[f"cb{l}"] = cb
+    np.savez(npz, **arrs)
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        env[k] = str(threads)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "PYTHONPATH"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, runner, "--npz", npz, "--device", device, "--threads", str(threads), "--repeat", str(repeat),
+                            "--bn", str(int(bn)), "--out", out], env=env, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=timeout_s)
+        if r.returncode != 0 or not os.path.exists(out):
+            return {"unavailable": f"runner exit {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.load(open(out))
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"runner exceeded {timeout_s} s"}
+
+
+def c2_cpu_baseline(n_batches, repeat, drop, bn):
+    ws, bs, wd, bd, cbs = c2_weights()
+    x = reference_items(n_batches * C2_BATCH)
+    res = run_reference_train(ws, bs, wd, bd, cbs, x, "cpu", repeat, host_cores(), bn)
+    if "unavailable" in res:
+        return {"value": None, "unit": "items/s", "cores": host_cores(), "kind": "reference", "sample": res["unavailable"]}, None
+    secs = res["seconds"][drop:]
+    dt = float(np.mean(secs))
+    return {"value": res["items"] / dt, "unit": "items/s", "cores": int(res["torch_threads"]), "kind": "reference", "seconds": dt,
+            "host_cpus": res["cpu_count"], "torch": res["torch"],
+            "sample": f"{n_batches} batches of {C2_BATCH} ({res['items']} items) per run: the UNMODIFIED Trainer._train_epoch "
+                      f"(baseline/_ref/index/trainer.py:98-125, torch CPU), {len(secs)} timed run(s)"}, dt
+
+
+def run_c2_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    nb = c2_reference_batches(a.steps, a.warmup)
+    cpu, dt = c2_cpu_baseline(nb, a.warmup + a.steps, a.warmup, a.bn)
+    line = {"impl": "reference", "metric": "items trained/sec (RQ-VAE training epoch, batch 1024)", "value": cpu["value"], "unit": "items/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": None if dt is None else dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": c2_config(a.gpus, a.steps, a.warmup, a.bn),
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_c2(a):
+    """One step = one training epoch through lcrec_b200.trainer.Trainer._train_epoch (the reference's loop, trainer.py:98-125)."""
+    import torch
+    from lcrec_b200 import ops
+    from lcrec_b200.models import RQVAE
+    import lcrec_b200.trainer as TR
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --config c2 measures the single-GPU epoch; the data-parallel trainer is scripts/check_dp_trainer.py")
+    device = torch.device("cuda:0")
+    torch.cuda.set_device(device)
+    pk = peaks()
+    ws, bs, wd, bd, cbs = c2_weights()
+
+    def build(bn):
+        m = RQVAE(in_dim=DIMS[0], num_emb_list=N_CODES, e_dim=E_DIM, layers=DIMS[1:-1], bn=bn, kmeans_init=False,
+                  sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST], sk_iters=SK_ITERS)
+        sd = m.state_dict()
+        stride = 4 if bn else 3
+        for i, (w, b, w2, b2) in enumerate(zip(ws, bs, wd, bd)):
+            sd[f"encoder.mlp_layers.{1 + stride * i}.weight"] = torch.from_numpy(w); sd[f"encoder.mlp_layers.{1 + stride * i}.bias"] = torch.from_numpy(b)
+            sd[f"decoder.mlp_layers.{1 + stride * i}.weight"] = torch.from_numpy(w2); sd[f"decoder.mlp_layers.{1 + stride * i}.bias"] = torch.from_numpy(b2)
+        for l, cb in enumerate(cbs):
+            sd[f"rq.vq_layers.{l}.embedding.weight"] = torch.from_numpy(cb)
+        m.load_state_dict(sd)
+        args = argparse.Namespace(lr=1e-3, epochs=10000, batch_size=C2_BATCH, num_workers=0, eval_step=50, learner="AdamW",
+                                  lr_scheduler_type="linear", warmup_epochs=50, data_path="", weight_decay=1e-4, dropout_prob=0.0, bn=bn,
+                                  loss_type="mse", kmeans_init=False, kmeans_iters=100, sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST], sk_iters=SK_ITERS,
+                                  device="cuda:0", num_emb_list=N_CODES, e_dim=E_DIM, quant_loss_weight=1.0, beta=0.25, layers=DIMS[1:-1],
+                                  save_limit=5, ckpt_dir=tempfile.mkdtemp(prefix="lcrec_c2_"))
+        return TR.Trainer(args, m, 25)
+
+    import logging
+    logging.disable(logging.CRITICAL)
+    xh = torch.from_numpy(reference_items(C2_ITEMS)).pin_memory()
+    host_loader = [xh[s:s + C2_BATCH] for s in range(0, C2_ITEMS, C2_BATCH)]
+    xd = xh.to(device)
+    dev_loader = [xd[s:s + C2_BATCH] for s in range(0, C2_ITEMS, C2_BATCH)]
+    os.environ.setdefault("TQDM_DISABLE", "1")
+
+    def timed(tr, loader, steps, warmup):
+        with open(os.devnull, "w") as devnull, contextlib_redirect(devnull):
+            for ep in range(warmup):
+                tr._train_epoch(loader, ep)
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for ep in range(steps):
+                losses = tr._train_epoch(loader, warmup + ep)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, ops.launch_count() - n0, losses
+
+    tr = build(a.bn)
+    sampler = ClockSampler(0)
+    ms_step, launches, losses = timed(tr, dev_loader, a.steps, a.warmup)
+    clocks = sampler.stop()
+    ms_e2e, _, _ = timed(tr, host_loader, max(1, min(a.steps, 3)), 1)
+    g = tr._gstep
+    extra = {}
+    if not a.no_cpu:
+        other = build(not a.bn)
+        ms_other, _, _ = timed(other, dev_loader, 2, 2)
+        extra["bn_" + str(not a.bn).lower() + "_ms_per_step"] = ms_other
+        del other
+        monkey = TR.TRAIN_GRAPH
+        TR.TRAIN_GRAPH = False
+        eager = build(a.bn)
+        ms_eager, _, _ = timed(eager, dev_loader, 2, 1)
+        TR.TRAIN_GRAPH = monkey
+        extra["eager_launches_ms_per_step"] = ms_eager
+        del eager
+    value = C2_ITEMS / (ms_step * 1e-3)
+    ach = value * C2_FLOP_PER_ITEM / 1e12
+    cpu = None
+    if not a.no_cpu:
+        cpu, _ = c2_cpu_baseline(12, 1, 0, a.bn)
+    line = {"metric": "items trained/sec (RQ-VAE training epoch, batch 1024)", "value": value, "unit": "items/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "ms_per_batch": ms_step / len(dev_loader), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic (low-rank parents + noise, seeded weights)",
+            "config": c2_config(1, a.steps, a.warmup, a.bn), "clocks": clocks,
+            "e2e": {"value": C2_ITEMS / (ms_e2e * 1e-3), "unit": "items/s", "h2d_bytes_per_step": C2_ITEMS * DIMS[0] * 4, "d2h_bytes_per_step": 25 * 32,
+                    "note": "Trainer._train_epoch over pinned host batches: H2D of every batch and the per-step loss read-back inside the timed region"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole training step (encoder + decoder GEMMs forward, dgrad, wgrad; 3 MMAs per fp32 product)",
+                         "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                         "peak_source": pk["source"] + ", bf16 dense sustained",
+                         "note": "algorithmic FLOPs 134.3 MFLOP/item (SURVEY 8(d)) / epoch time; ceiling = peak / 3 (fp32-accurate operand split); "
+                                 "at batch 1024 the GEMMs fill 32 of 74 CTA-pair tiles, so the step is latency / occupancy bound, not pipe bound"},
+            "cpu_baseline": cpu, "losses_last_epoch": [float(v) for v in losses],
+            "cuda_graph": None if g is None else {"replays": g.replays, "eager_steps": g.eager_steps, "capture_error": g.capture_error},
+            **extra}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+class contextlib_redirect:
+    """stderr -> a sink (tqdm bars of the trainer), stdout untouched."""
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        self.old = sys.stderr
+        sys.stderr = self.sink
+
+    def __exit__(self, *exc):
+        sys.stderr = self.old
+        return False
 
 
 def main():
@@ -449,13 +693,27 @@ def main():
                     help="items per run of the unmodified reference script: default 25000 (C1) for the cpu_baseline leg of the GPU arm, "
                          "reference_sample_items(steps, warmup) per step for --impl reference")
     ap.add_argument("--engine", type=int, default=1, choices=[0, 1], help="GEMM operand encoding: 1 = f16 x3 (default), 0 = tf32 x3")
+    ap.add_argument("--check-items", dest="check_items", type=int, default=200_000,
+                    help="N > 1: items of the untimed sharded-vs-single-GPU equality check (over all ranks)")
     ap.add_argument("--no-e2e", dest="no_e2e", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--no-torch-cuda", dest="no_torch_cuda", action="store_true", help="skip the reference-on-torch-CUDA comparator")
     ap.add_argument("--profile-window", dest="profile_window", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2", "c5"],
+                    help="c3: index generation, 4 x 256 codes (default; BASELINE configs[2] / [3]); c5: 4 x 8192 codes, e_dim 256 "
+                         "(configs[4]; --items defaults to 100000); c2: the training epoch (configs[1])")
+    ap.add_argument("--bn", action="store_true", help="c2: BatchNorm in the encoder / decoder (what `run.sh --bn False` really trains)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 0)
+    set_config(a.config)
+    if a.config == "c5":
+        if a.items == 1_000_000:
+            a.items = 100_000
+        a.e2e_items = min(a.e2e_items, a.items)
+        a.cpu_sample = a.cpu_sample or 4096       # the reference's per-group Sinkhorn over 8192 columns is ~40x the c3 cost per row
+    if a.config == "c2":
+        return run_c2_reference(a) if a.impl == "reference" else run_c2(a)
     if a.impl == "reference":
         return run_reference_arm(a)
     return run_gpu_arm(a)

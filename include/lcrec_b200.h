@@ -143,6 +143,49 @@ int lcrec_adam_clip_step(int n_tensors, float* const* params, float* const* grad
                          double weight_decay, int decoupled, int64_t step, double max_norm, int write_clipped_grads,
                          float* total_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same update with its three per-step scalars {1 - lr wd, lr / (1 - beta1^t), sqrt(1 - beta2^t)} (lcrec_adam_hyper writes
+ * them to HOST memory) read from DEVICE memory: the launches of a training step can be captured ONCE in a CUDA graph and
+ * replayed while the schedule of index/trainer.py:83-92,120 advances; the caller refreshes hyper_dev before each replay. */
+int lcrec_adam_hyper(double lr, double beta1, double beta2, double weight_decay, int64_t step, float* out3_host);
+int lcrec_adam_clip_step_dev(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const int64_t* numel, const float* hyper_dev, double beta1, double beta2,
+                             double eps, double weight_decay, int decoupled, double max_norm, int write_clipped_grads,
+                             float* total_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- a2 (training): BatchNorm1d in training mode + the ReLU behind it (index/models/layers.py:25-29; `run.sh --bn False`
+ * parses to bn=True, index/main.py:31) -----------------------------------------------------------------------------------
+ * y (n_rows, n_channels) fp32 row-major = the Linear output.  Two launches each way with the per-channel fp64 sums in
+ * between, so that a data-parallel job can all-reduce them (synchronised BN = single-device global-batch semantics):
+ *   forward_reduce : sums[s][0][c] = sum_rows y, sums[s][1][c] = sum_rows y^2 for s < lcrec_bn_splits(n_rows, n_channels)
+ *                    row blocks (sums: lcrec_bn_sums_elems(n_channels) doubles);
+ *   forward_apply  : mean, biased variance over n_rows_total (>= n_rows: pass the global count and ONE block of reduced sums
+ *                    under DP), out = relu?((y - mean) / sqrt(var + eps) * gamma + beta), save_mean / save_invstd (C) for the
+ *                    backward, running_mean / running_var (nullable) <- (1 - momentum) r + momentum stat (unbiased variance),
+ *                    exactly torch.nn.BatchNorm1d;
+ *   backward_reduce: sums = {sum g, sum g xhat}, g = gy * (out > 0) when relu, xhat = (y - mean) invstd;
+ *   backward_apply : g_beta, g_gamma (nullable) and gx (nullable) = gamma invstd (g - g_beta / N - xhat g_gamma / N). */
+int64_t lcrec_bn_sums_elems(int n_channels);
+int lcrec_bn_splits(int64_t n_rows, int n_channels);
+int lcrec_bn_forward_reduce(const float* y, int64_t n_rows, int n_channels, double* sums, void* stream);
+int lcrec_bn_forward_apply(const float* y, const double* sums, int n_splits, int64_t n_rows, int64_t n_rows_total,
+                           int n_channels, const float* gamma, const float* beta, double eps, double momentum, int relu,
+                           float* out, float* save_mean, float* save_invstd, float* running_mean, float* running_var,
+                           void* stream);
+int lcrec_bn_backward_reduce(const float* y, const float* gy, const float* out, int relu, const float* save_mean,
+                             const float* save_invstd, int64_t n_rows, int n_channels, double* sums, void* stream);
+int lcrec_bn_backward_apply(const float* y, const float* gy, const float* out, int relu, const double* sums, int n_splits,
+                            int64_t n_rows, int64_t n_rows_total, int n_channels, const float* gamma, const float* save_mean,
+                            const float* save_invstd, float* gx, float* g_gamma, float* g_beta, void* stream);
+
+/* ---- a10 (training): reconstruction loss of RQVAE.compute_loss (index/models/rqvae.py:74-85) ---------------------------
+ * loss (1 fp32, device) = mean over `total` = n * in_dim elements of (out - x)^2 (loss_type 0, F.mse_loss) or |out - x|
+ * (1, F.l1_loss); fp64 partial sums in a fixed order.  backward: grad = (*upstream, or 1 when NULL) * d loss / d out. */
+int64_t lcrec_recon_loss_workspace_bytes(int64_t total);
+int lcrec_recon_loss(const float* out, const float* x, int64_t total, int loss_type, float* loss, void* ws, int64_t ws_bytes,
+                     void* stream);
+int lcrec_recon_loss_backward(const float* out, const float* x, int64_t total, int loss_type, const float* upstream,
+                              float* grad, void* stream);
+
 /* ---- a4: distances only (index/models/vq.py:71-73), (n, K) fp32 ------------------------ */
 int lcrec_vq_distances(const float* r, int64_t n, int e_dim, const float* codebook, int n_codes,
                        float* d, void* stream);
@@ -331,6 +374,13 @@ int64_t lcrec_masked_mean_pool_workspace_bytes(int64_t n_seq, int64_t seq_len, i
 int lcrec_masked_mean_pool(const void* hidden, int dtype, const int64_t* mask, int64_t n_seq, int64_t seq_len,
                            int hidden_dim, float* out, int64_t out_stride, int accumulate, double divide_by,
                            void* workspace, int64_t workspace_bytes, void* stream);
+/* ---- a16 / f2: `.index.json` text on the device (index/generate_indices.py:83,138-145) -------------------------------
+ * The bytes json.dump({item: ["<a_%d>", "<b_%d>", ...]}) writes (int keys as strings, separators ", " and ": "), formatted
+ * from the code table in HBM: out (device, out_cap bytes; NULL for a sizing call), total_bytes_dev (1 int64, device) = the
+ * exact length; nothing is written past out_cap.  n_levels <= 5 (the reference's prefix list). */
+int64_t lcrec_index_json_workspace_bytes(int64_t n);
+int lcrec_index_json(const int64_t* codes, int64_t n, int n_levels, char* out, int64_t out_cap, int64_t* total_bytes_dev,
+                     void* ws, int64_t ws_bytes, void* stream);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).
  * Tags: 0 = operand split of the input, 1+l = MLP layer l, 17 = splits of the tail layers, 20 = fused RQ,
  * 21 = collision checks, 22 / 23 = per-group Sinkhorn of the first / the later rounds.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */

@@ -88,6 +88,20 @@ SIGNATURES = {
     "lcrec_adam_workspace_bytes": (i64, [C.c_int, C.POINTER(i64)]),
     "lcrec_adam_clip_step": (C.c_int, [C.c_int, pp, pp, pp, pp, C.POINTER(i64), f64, f64, f64, f64, f64, C.c_int, i64, f64,
                                        C.c_int, vp, vp, i64, vp]),
+    "lcrec_adam_hyper": (C.c_int, [f64, f64, f64, f64, i64, C.POINTER(C.c_float)]),
+    "lcrec_adam_clip_step_dev": (C.c_int, [C.c_int, pp, pp, pp, pp, C.POINTER(i64), vp, f64, f64, f64, f64, C.c_int, f64,
+                                           C.c_int, vp, vp, i64, vp]),
+    "lcrec_bn_sums_elems": (i64, [C.c_int]),
+    "lcrec_bn_splits": (C.c_int, [i64, C.c_int]),
+    "lcrec_bn_forward_reduce": (C.c_int, [vp, i64, C.c_int, vp, vp]),
+    "lcrec_bn_forward_apply": (C.c_int, [vp, vp, C.c_int, i64, i64, C.c_int, vp, vp, f64, f64, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "lcrec_bn_backward_reduce": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, i64, C.c_int, vp, vp]),
+    "lcrec_bn_backward_apply": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, i64, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "lcrec_recon_loss_workspace_bytes": (i64, [i64]),
+    "lcrec_recon_loss": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, i64, vp]),
+    "lcrec_recon_loss_backward": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, vp]),
+    "lcrec_index_json_workspace_bytes": (i64, [i64]),
+    "lcrec_index_json": (C.c_int, [vp, i64, C.c_int, vp, i64, vp, vp, i64, vp]),
     "lcrec_kmeanspp_workspace_bytes": (i64, [i64, C.c_int]),
     "lcrec_kmeanspp_seed": (C.c_int, [vp, i64, C.c_int, C.c_int, i64, vp, C.c_int, vp, vp, vp, i64, vp]),
     "lcrec_indexer_codes": (vp, [vp]),

@@ -12,9 +12,29 @@
 
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>     // header-only in CUDA 12: ranges cost a few ns unless a tool (nsys / ncu --nvtx) is attached
+
 #include "common.cuh"
 
 namespace lcrec {
+
+// NVTX range per stage (tracing row): every ProfScope of the library is also an NVTX range named after its tag
+static const char* stage_name(int tag) {
+  static const char* mlp[] = {"lcrec/mlp_layer1", "lcrec/mlp_layer2", "lcrec/mlp_layer3", "lcrec/mlp_layer4", "lcrec/mlp_layer5",
+                              "lcrec/mlp_layer6", "lcrec/mlp_layer7", "lcrec/mlp_layer8+"};
+  if (tag == 0) return "lcrec/input_operand_split";
+  if (tag >= 1 && tag <= 16) return mlp[tag - 1 < 7 ? tag - 1 : 7];
+  switch (tag) {
+    case 17: return "lcrec/tail_operand_splits";
+    case 20: return "lcrec/rq_quantize";
+    case 21: return "lcrec/collision_check";
+    case 22: return "lcrec/sinkhorn_groups_round1";
+    case 23: return "lcrec/sinkhorn_groups_later_rounds";
+    case 24: return "lcrec/sinkhorn_warp_classes";
+    case 26: return "lcrec/sinkhorn_literal_rerun";
+    default: return "lcrec/stage";
+  }
+}
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
@@ -51,12 +71,14 @@ static cudaEvent_t prof_event() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 void prof_begin(int tag, cudaStream_t st) {
+  nvtxRangePushA(stage_name(tag));
   if (!g_prof_on || tag < 0 || tag >= kProfTags) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, st);
   g_prof_open[tag] = e;
 }
 void prof_end(int tag, cudaStream_t st) {
+  nvtxRangePop();
   if (!g_prof_on || tag < 0 || tag >= kProfTags || !g_prof_open[tag]) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, st);

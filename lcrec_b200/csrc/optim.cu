@@ -68,6 +68,8 @@ struct AdamArgs {
   float max_norm;         // <= 0: no clipping
   int decoupled;          // 1 = AdamW (p *= 1 - lr wd), 0 = Adam (g += wd p)
   int write_grad;         // store the clipped gradient back
+  const float* hyper;     // nullable, device: {decay, step_size, bc2_sqrt} of THIS step; overrides the three fields above so that
+                          // a captured CUDA graph of the training step can be replayed with a new learning rate / step count
 };
 
 __global__ void __launch_bounds__(kOptThreads)
@@ -102,7 +104,10 @@ adam_step_kernel(OptTable t, AdamArgs a, const double* __restrict__ partial, int
   float* __restrict__ g = t.g[ti];
   float* __restrict__ m = t.m[ti];
   float* __restrict__ v = t.v[ti];
-  const float one_minus_b1 = a.one_minus_b1, one_minus_b2 = a.one_minus_b2, decay = a.decay;
+  const float one_minus_b1 = a.one_minus_b1, one_minus_b2 = a.one_minus_b2;
+  const float decay = a.hyper ? a.hyper[0] : a.decay;
+  const float step_size = a.hyper ? a.hyper[1] : a.step_size;
+  const float bc2_sqrt = a.hyper ? a.hyper[2] : a.bc2_sqrt;
   for (long long i = base + threadIdx.x; i < end; i += kOptThreads) {
     float gi = g[i];
     float pi = p[i];
@@ -114,8 +119,8 @@ adam_step_kernel(OptTable t, AdamArgs a, const double* __restrict__ partial, int
     else if (a.weight_decay != 0.f) gi = fmaf(pi, a.weight_decay, gi);   // grad.add(param, alpha=weight_decay)
     const float mi = fmaf(__fsub_rn(gi, m[i]), one_minus_b1, m[i]);       // exp_avg.lerp_(grad, 1 - beta1)
     const float vi = fmaf(__fmul_rn(gi, gi), one_minus_b2, __fmul_rn(v[i], a.beta2));   // mul_(beta2).addcmul_(g, g, 1 - beta2)
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), a.bc2_sqrt), a.eps);
-    pi = fmaf(-a.step_size, __fdiv_rn(mi, denom), pi);                    // addcdiv_(exp_avg, denom, value=-step_size)
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), a.eps);
+    pi = fmaf(-step_size, __fdiv_rn(mi, denom), pi);                    // addcdiv_(exp_avg, denom, value=-step_size)
     m[i] = mi;
     v[i] = vi;
     p[i] = pi;
@@ -132,11 +137,20 @@ extern "C" int64_t lcrec_adam_workspace_bytes(int n_tensors, const int64_t* nume
   return arena_need(blocks * 8) + 256;
 }
 
-extern "C" int lcrec_adam_clip_step(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
-                                    float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2,
-                                    double eps, double weight_decay, int decoupled, int64_t step, double max_norm,
-                                    int write_clipped_grads, float* total_norm_out, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
+// The three per-step scalars of the update as the kernel consumes them (fp32): {1 - lr * wd, lr / (1 - beta1^t), sqrt(1 - beta2^t)}
+extern "C" int lcrec_adam_hyper(double lr, double beta1, double beta2, double weight_decay, int64_t step, float* out3_host) {
+  LC_ARG(out3_host && step >= 1);
+  out3_host[0] = (float)(1.0 - lr * weight_decay);
+  out3_host[1] = (float)(lr / (1.0 - pow(beta1, (double)step)));
+  out3_host[2] = (float)sqrt(1.0 - pow(beta2, (double)step));
+  return LCREC_OK;
+}
+
+static int adam_clip_step_impl(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                               float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2,
+                               double eps, double weight_decay, int decoupled, int64_t step, double max_norm,
+                               int write_clipped_grads, float* total_norm_out, const float* hyper_dev, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
   LC_ARG(n_tensors >= 0 && step >= 1);
   if (n_tensors == 0) return LCREC_OK;
   LC_ARG(params && grads && exp_avg && exp_avg_sq && numel);
@@ -161,6 +175,7 @@ extern "C" int lcrec_adam_clip_step(int n_tensors, float* const* params, float* 
   a.max_norm = (float)max_norm;
   a.decoupled = decoupled;
   a.write_grad = write_clipped_grads;
+  a.hyper = hyper_dev;
 
   // two sweeps over the tensor list in groups that fit the kernel-argument table: all partial sums first, then the updates
   for (int pass = max_norm > 0 ? 0 : 1; pass < 2; ++pass) {
@@ -191,4 +206,26 @@ extern "C" int lcrec_adam_clip_step(int n_tensors, float* const* params, float* 
     }
   }
   return LCREC_OK;
+}
+
+extern "C" int lcrec_adam_clip_step(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                                    float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2,
+                                    double eps, double weight_decay, int decoupled, int64_t step, double max_norm,
+                                    int write_clipped_grads, float* total_norm_out, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  return adam_clip_step_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, decoupled, step,
+                             max_norm, write_clipped_grads, total_norm_out, nullptr, workspace, workspace_bytes, stream);
+}
+
+// Same update with the per-step scalars read from DEVICE memory (hyper_dev: 3 fp32 as lcrec_adam_hyper computes them): the
+// launches can be captured once in a CUDA graph and replayed while the learning-rate schedule and the step count advance -
+// the caller refreshes hyper_dev (one 12-byte copy on the same stream) before each replay.
+extern "C" int lcrec_adam_clip_step_dev(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                                        float* const* exp_avg_sq, const int64_t* numel, const float* hyper_dev, double beta1,
+                                        double beta2, double eps, double weight_decay, int decoupled, double max_norm,
+                                        int write_clipped_grads, float* total_norm_out, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+  LC_ARG(hyper_dev != nullptr);
+  return adam_clip_step_impl(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, 1e-3, beta1, beta2, eps, weight_decay, decoupled, 1,
+                             max_norm, write_clipped_grads, total_norm_out, hyper_dev, workspace, workspace_bytes, stream);
 }

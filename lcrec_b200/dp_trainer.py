@@ -14,8 +14,9 @@ things cross NVLink, as the north star asks:
   (``lcrec_adam_clip_step``), so the replicas never diverge.
 
 Codebook k-means initialisation (first batch, ``vq.py:67-68``) runs on the full global batch on every rank with the same
-numpy seed, after which rank 0's codebooks are broadcast.  BatchNorm in training mode would need synchronised batch
-statistics and is refused, and so is the EMA-codebook variant of index_improve/ (its in-place per-rank updates would make the
+numpy seed, after which rank 0's codebooks are broadcast.  BatchNorm in training mode runs SYNCHRONISED: its kernels all-reduce the
+per-channel sums of the forward and of the backward pass over the ranks (global-batch statistics, identical running
+statistics everywhere).  Refused: the EMA-codebook variant of index_improve/ (its in-place per-rank updates would make the
 replicas diverge).  A rank whose row block is empty still joins the Sinkhorn collectives.  Rank 0 writes checkpoints.
 """
 from __future__ import annotations
@@ -38,9 +39,9 @@ class DataParallelTrainer(Trainer):
         self.group = group if group is not None else dist.group.WORLD
         self.rank = dist.get_rank(self.group)
         self.world = dist.get_world_size(self.group)
-        if any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in model.modules()):
-            raise NotImplementedError("data-parallel training with BatchNorm needs synchronised batch statistics "
-                                      "(the single-device global-batch semantics of the reference); use bn=False")
+        # BatchNorm (what `run.sh --bn False` really trains, main.py:31): the single-device semantics need batch statistics
+        # over the GLOBAL batch -> the BN kernels all-reduce their per-channel sums over the group (forward and backward)
+        self._bn_modules = [m for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
         if any(name.endswith("_ema_cluster_size") for name, _ in model.named_buffers()):
             # index_improve's EMA codebooks are updated in place from the rows a rank sees (lcrec_ema_update): with sharded
             # rows the replicas' counts, sums and codebooks would drift apart from step 1, and the dead-code reset draws
@@ -100,12 +101,20 @@ class DataParallelTrainer(Trainer):
         saved = [(q, q.dist_sinkhorn) for q in rq.vq_layers if getattr(q, "dist_sinkhorn", None) is not None]
         for q, _ in saved:
             q.dist_sinkhorn = None
+        bn_saved = [(bn, getattr(bn, "lcrec_sync", None), {k: v.clone() for k, v in bn.state_dict().items() if "running" in k or "tracked" in k})
+                    for bn in getattr(self, "_bn_modules", [])]
+        for bn, _, _ in bn_saved:
+            bn.lcrec_sync = None                                # the full batch is local in this pass
         try:
             with torch.no_grad():
                 self.model(data.to(self.device))
         finally:
             for q, ds in saved:
                 q.dist_sinkhorn = ds
+            for bn, sync, bufs in bn_saved:                     # this extra forward must not count as a training step of the BN layers
+                bn.lcrec_sync = sync
+                for k, v in bufs.items():
+                    getattr(bn, k).copy_(v)
         src = dist.get_global_rank(self.group, 0) if self.group is not dist.group.WORLD else 0
         for q in rq.vq_layers:
             if hasattr(q, "embedding"):
@@ -134,6 +143,11 @@ class DataParallelTrainer(Trainer):
             weight = local.shape[0] / max(n, 1)
             for q in self._sinkhorn_levels:
                 q.dist_sinkhorn.n_rows_hint = n                 # the global row count, known here: no all-reduce + host read
+            if self._bn_modules:
+                if n < self.world:
+                    raise RuntimeError(f"synchronised BatchNorm: a batch of {n} rows leaves a rank of {self.world} without rows")
+                for bn in self._bn_modules:
+                    bn.lcrec_sync = (self.group, n) if self.device.type == "cuda" else None
             with ops.defer_checks():
                 self.optimizer.zero_grad()
                 self._init_codebooks_on_global_batch(data)

@@ -9,7 +9,8 @@ reference checkpoints), but the arithmetic runs in liblcrec_b200.so:
   fused bias + ReLU, activations handed from layer to layer already split; eval-mode BatchNorm is folded
   into the weights;
 * training: each ``nn.Linear`` (+ReLU when nothing sits between them) goes through the same GEMM
-  kernel inside an autograd Function; BatchNorm / Dropout / non-ReLU activations stay torch modules.
+  kernel inside an autograd Function; training-mode BatchNorm1d (+ReLU) runs on its own reduce / apply kernels
+  (``_BnReluFn``, synchronised over a process group on request); Dropout / non-ReLU activations stay torch modules.
 
 CUDA only - a CPU tensor raises (no fallback).
 """
@@ -57,6 +58,42 @@ class _LinearFn(torch.autograd.Function):
                                          need_gx=ctx.needs_input_grad[0], need_gw=ctx.needs_input_grad[1],
                                          need_gb=ctx.has_bias and ctx.needs_input_grad[2])
         return gx, gw, gb, None
+
+
+class _BnReluFn(torch.autograd.Function):
+    """Training-mode BatchNorm1d + the ReLU behind it (reference layers.py:25-29) on the kernels of csrc/train_extra.cu:
+    batch statistics, running-statistics update (momentum / cumulative average exactly like torch), analytic backward.
+    ``bn.lcrec_sync = (group, n_total)`` (set by the data-parallel trainer) all-reduces the per-channel sums over the ranks."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bn, relu: bool):
+        sync = getattr(bn, "lcrec_sync", None)
+        group, n_total = sync if sync is not None else (None, None)
+        factor = 0.0
+        rm = rv = None
+        if bn.track_running_stats and bn.running_mean is not None:
+            rm, rv = bn.running_mean, bn.running_var
+            if bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            if bn.momentum is None:                              # cumulative moving average: needs the count on the host
+                factor = 1.0 / float(bn.num_batches_tracked.item())
+            else:
+                factor = float(bn.momentum)
+        out, mean, invstd = ops.bn_relu_forward(y, gamma, beta, rm, rv, factor, bn.eps, relu, group=group, n_total=n_total)
+        if rm is not None:                                       # written through raw pointers: version-keyed caches must see it
+            from ..optim import _bump_versions
+            _bump_versions([rm, rv])
+        ctx.save_for_backward(y, out if relu else None, gamma, mean, invstd)
+        ctx.relu, ctx.sync = relu, (group, n_total)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, out, gamma, mean, invstd = ctx.saved_tensors
+        need_gp = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gx, gg, gb = ops.bn_relu_backward(y, gy, out, ctx.relu, gamma, mean, invstd, need_gx=ctx.needs_input_grad[0],
+                                          need_gp=need_gp, group=ctx.sync[0], n_total=ctx.sync[1])
+        return gx, (gg if ctx.needs_input_grad[1] else None), (gb if ctx.needs_input_grad[2] else None), None, None
 
 
 class _MlpFn(torch.autograd.Function):
@@ -209,7 +246,12 @@ class MLPLayers(nn.Module):
             fuse = bn is None and isinstance(act, nn.ReLU)
             x = _LinearFn.apply(x, lin.weight, lin.bias, fuse)
             if bn is not None:
-                x = bn(x)
+                if bn.training or not bn.track_running_stats:     # batch statistics: the BN + ReLU kernels
+                    fuse = isinstance(act, nn.ReLU)
+                    lead = x.shape
+                    x = _BnReluFn.apply(x.reshape(-1, lead[-1]), bn.weight, bn.bias, bn, fuse).reshape(lead)
+                else:
+                    x = bn(x)                                     # eval statistics with autograd on (not a training path)
             if act is not None and not fuse:
                 x = act(x)
         return x

@@ -11,6 +11,27 @@ from .layers import MLPLayers
 from .rq import ResidualVectorQuantizer
 
 
+class _ReconLossFn(torch.autograd.Function):
+    """``F.mse_loss`` / ``F.l1_loss`` (mean) of rqvae.py:77-80 and its backward on lcrec_recon_loss / _backward."""
+
+    @staticmethod
+    def forward(ctx, out, xs, loss_type: str):
+        from .. import ops
+        ctx.save_for_backward(out, xs)
+        ctx.loss_type = loss_type
+        return ops.recon_loss(out.detach(), xs.detach(), loss_type)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import ops
+        out, xs = ctx.saved_tensors
+        go = ops.recon_loss_backward(out, xs, ctx.loss_type, g) if ctx.needs_input_grad[0] else None
+        gx = None
+        if ctx.needs_input_grad[1]:
+            gx = -(go if go is not None else ops.recon_loss_backward(out, xs, ctx.loss_type, g))
+        return go, gx, None
+
+
 class RQVAE(nn.Module):
     _LOSSES = {"mse": F.mse_loss, "l1": F.l1_loss}
     _RQ = ResidualVectorQuantizer
@@ -53,5 +74,8 @@ class RQVAE(nn.Module):
         recon_fn = self._LOSSES.get(self.loss_type)
         if recon_fn is None:
             raise ValueError("incompatible loss type")           # rqvae.py:81
-        loss_recon = recon_fn(out, xs, reduction="mean")
+        if out.is_cuda and out.dtype == torch.float32 and xs.dtype == torch.float32 and out.shape == xs.shape:
+            loss_recon = _ReconLossFn.apply(out, xs, self.loss_type)
+        else:
+            loss_recon = recon_fn(out, xs, reduction="mean")
         return loss_recon + self.quant_loss_weight * quant_loss, loss_recon

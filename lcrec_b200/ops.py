@@ -94,6 +94,24 @@ def check_later(kind: str, word: torch.Tensor) -> None:
         _evaluate_check(kind, word)
 
 
+def take_pending() -> List[Tuple[str, torch.Tensor]]:
+    """Hand the queued status words to the caller WITHOUT reading them (a step captured in a CUDA graph keeps the tensors
+    and evaluates them after each replay)."""
+    pending, _PENDING[:] = list(_PENDING), []
+    return pending
+
+
+def evaluate_check_value(kind: str, v: int) -> None:
+    """The check of `_evaluate_check` on a value that is already on the host."""
+    if kind == "amplitude" and v != 0:
+        raise AssertionError("amplitude > 0")
+    if kind == "sinkhorn":
+        if v & 8:
+            raise RuntimeError("distributed Sinkhorn: a peer rank did not arrive")
+        if v & 1:
+            print("Sinkhorn Algorithm returns nan/inf values.")
+
+
 def flush_checks() -> None:
     pending, _PENDING[:] = list(_PENDING), []
     for kind, word in pending:
@@ -170,6 +188,8 @@ class MlpHandle:
         y = torch.empty((n, self.dims[-1]), dtype=torch.float32, device=x2.device)
         need = int(self.lib.lcrec_mlp_workspace_bytes(self.handle, n))
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != x2.device:
+            if self._workspace is not None:                  # a captured CUDA graph may still point at the old one
+                self.__dict__.setdefault("_retired", []).append(self._workspace)
             self._workspace = _ws(need, x2.device)
         acts = None
         acts_arr = None
@@ -251,6 +271,95 @@ def linear_backward(x: torch.Tensor, w: torch.Tensor, y_relu: Optional[torch.Ten
         _lib.check(lib.lcrec_linear_backward(_p(x2), _p(w2), _p(y2), _p(g2), n, k, m, _p(gx), _p(gw), _p(gb), _p(ws),
                                              ws.numel(), _stream(x2)))
     return (None if gx is None else gx.reshape(x.shape)), gw, gb
+
+
+# --------------------------------------------------------------------------- BatchNorm (training) + reconstruction loss
+def bn_relu_forward(y: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor],
+                    running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor], momentum: float, eps: float,
+                    relu: bool, group=None, n_total: Optional[int] = None):
+    """Training-mode ``BatchNorm1d`` (+ the ReLU behind it, layers.py:25-29) of a (n, C) Linear output: returns
+    (out, save_mean, save_invstd) and updates the running statistics in place.  ``group``: all-reduce the per-channel sums
+    over a process group (synchronised BN; ``n_total`` = the global row count, known to the caller)."""
+    _need_cuda(y)
+    lib = _lib.load()
+    y2 = _f32c(y)
+    n, c = y2.shape
+    sums = torch.empty(int(lib.lcrec_bn_sums_elems(c)), dtype=torch.float64, device=y2.device)
+    out = torch.empty_like(y2)
+    mean = torch.empty(c, dtype=torch.float32, device=y2.device)
+    invstd = torch.empty(c, dtype=torch.float32, device=y2.device)
+    splits = int(lib.lcrec_bn_splits(n, c))
+    with torch.cuda.device(y2.device):
+        _lib.check(lib.lcrec_bn_forward_reduce(_p(y2), n, c, _p(sums), _stream(y2)))
+        if group is not None:
+            import torch.distributed as dist
+            red = sums[: splits * 2 * c].view(splits, 2 * c).sum(0)
+            dist.all_reduce(red, group=group)
+            sums[: 2 * c] = red
+            splits = 1
+        tot = int(n_total) if n_total is not None else n
+        _lib.check(lib.lcrec_bn_forward_apply(_p(y2), _p(sums), splits, n, tot, c, _p(gamma), _p(beta), float(eps), float(momentum),
+                                              int(relu), _p(out), _p(mean), _p(invstd), _p(running_mean), _p(running_var), _stream(y2)))
+    return out, mean, invstd
+
+
+def bn_relu_backward(y: torch.Tensor, gy: torch.Tensor, out: torch.Tensor, relu: bool, gamma: Optional[torch.Tensor],
+                     mean: torch.Tensor, invstd: torch.Tensor, need_gx: bool = True, need_gp: bool = True, group=None,
+                     n_total: Optional[int] = None):
+    """(gx, g_gamma, g_beta) of the training-mode BatchNorm1d + ReLU above."""
+    _need_cuda(y, gy)
+    lib = _lib.load()
+    y2, g2 = _f32c(y), _f32c(gy)
+    n, c = y2.shape
+    sums = torch.empty(int(lib.lcrec_bn_sums_elems(c)), dtype=torch.float64, device=y2.device)
+    gx = torch.empty_like(y2) if need_gx else None
+    gg = torch.empty(c, dtype=torch.float32, device=y2.device) if need_gp else None
+    gb = torch.empty(c, dtype=torch.float32, device=y2.device) if need_gp else None
+    splits = int(lib.lcrec_bn_splits(n, c))
+    with torch.cuda.device(y2.device):
+        _lib.check(lib.lcrec_bn_backward_reduce(_p(y2), _p(g2), _p(out), int(relu), _p(mean), _p(invstd), n, c, _p(sums), _stream(y2)))
+        if group is not None:
+            # synchronised BN: gx needs the sums over the GLOBAL batch; g_gamma / g_beta stay this rank's LOCAL sums, because the
+            # trainer's gradient all-reduce (SUM over ranks) adds them up afterwards like every other parameter gradient
+            import torch.distributed as dist
+            red = sums[: splits * 2 * c].view(splits, 2 * c).sum(0)
+            if need_gp:
+                gb, gg = red[:c].to(torch.float32), red[c:].to(torch.float32)
+            dist.all_reduce(red, group=group)
+            sums[: 2 * c] = red
+            splits = 1
+        tot = int(n_total) if n_total is not None else n
+        _lib.check(lib.lcrec_bn_backward_apply(_p(y2), _p(g2), _p(out), int(relu), _p(sums), splits, n, tot, c, _p(gamma), _p(mean),
+                                               _p(invstd), _p(gx), _p(None if group is not None else gg),
+                                               _p(None if group is not None else gb), _stream(y2)))
+    return gx, gg, gb
+
+
+_LOSS_TYPES = {"mse": 0, "l1": 1}
+
+
+def recon_loss(out: torch.Tensor, x: torch.Tensor, loss_type: str) -> torch.Tensor:
+    """``F.mse_loss`` / ``F.l1_loss`` (reduction="mean") of rqvae.py:74-85 as a 0-dim fp32 tensor."""
+    _need_cuda(out, x)
+    lib = _lib.load()
+    o2, x2 = _f32c(out), _f32c(x)
+    assert o2.shape == x2.shape
+    loss = torch.empty((), dtype=torch.float32, device=o2.device)
+    ws = _ws(lib.lcrec_recon_loss_workspace_bytes(o2.numel()), o2.device)
+    with torch.cuda.device(o2.device):
+        _lib.check(lib.lcrec_recon_loss(_p(o2), _p(x2), o2.numel(), _LOSS_TYPES[loss_type], _p(loss), _p(ws), ws.numel(), _stream(o2)))
+    return loss
+
+
+def recon_loss_backward(out: torch.Tensor, x: torch.Tensor, loss_type: str, upstream: Optional[torch.Tensor]) -> torch.Tensor:
+    _need_cuda(out, x)
+    lib = _lib.load()
+    o2, x2 = _f32c(out), _f32c(x)
+    grad = torch.empty_like(o2)
+    up = None if upstream is None else upstream.detach().to(torch.float32).contiguous()
+    with torch.cuda.device(o2.device):
+        _lib.check(lib.lcrec_recon_loss_backward(_p(o2), _p(x2), o2.numel(), _LOSS_TYPES[loss_type], _p(up), _p(grad), _stream(o2)))
+    return grad.view(out.shape)
 
 
 # --------------------------------------------------------------------------- RQ
@@ -595,6 +704,26 @@ def sinkhorn_groups(resid: torch.Tensor, codebook: torch.Tensor, offsets: torch.
         off = (-ws.data_ptr()) % 256
         return int(flags[0].item()), int(ws[off + 8: off + 12].view(torch.int32).item())
     return int(flags[0].item())
+
+
+def index_json_bytes(codes: torch.Tensor) -> bytes:
+    """The `.index.json` text of a CUDA code table (n, L) int64 - the bytes ``json.dump`` writes at
+    generate_indices.py:144-145 - formatted on the device (lcrec_index_json) and copied to the host once."""
+    _need_cuda(codes)
+    lib = _lib.load()
+    c = codes.detach().to(torch.int64).contiguous()
+    n, L = c.shape
+    total = torch.zeros(1, dtype=torch.int64, device=c.device)
+    ws = _ws(lib.lcrec_index_json_workspace_bytes(n), c.device)
+    cap = 2 + n * (2 + 1 + 20 + 1 + 2 + 2 + L * (6 + 20 + 2))          # generous upper bound; most of it is never touched
+    if n <= 4_000_000:
+        cap = 2 + n * (2 + 1 + 7 + 1 + 2 + 2 + L * (6 + 20 + 2))
+    out = torch.empty(cap, dtype=torch.uint8, device=c.device)
+    with torch.cuda.device(c.device):
+        _lib.check(lib.lcrec_index_json(_p(c), n, L, _p(out), cap, _p(total), _p(ws), ws.numel(), _stream(c)))
+    nbytes = int(total.item())
+    assert nbytes <= cap
+    return out[:nbytes].cpu().numpy().tobytes()
 
 
 # --------------------------------------------------------------------------- whole generation

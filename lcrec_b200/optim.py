@@ -28,8 +28,40 @@ class FusedAdam(torch.optim.Optimizer):
                         maximize=False, foreach=None, capturable=False, differentiable=False, fused=None)
         super().__init__(params, defaults)
 
+    # ---- device-resident per-step scalars (CUDA-graph replay of the training step)
+    def prepare_hyper(self) -> None:
+        """Advance every parameter's step count and publish this step's scalars {1 - lr wd, lr / (1 - beta1^t),
+        sqrt(1 - beta2^t)} to the device (pinned ring -> 12-byte async copy on the current stream).  The following
+        ``clip_and_step(..., device_hyper=True)`` - eager or replayed from a captured graph - reads them from there, so the
+        learning-rate schedule and the bias corrections keep advancing although the launches are frozen in the graph."""
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FusedAdam.prepare_hyper: one parameter group expected")
+        group = self.param_groups[0]
+        ps = [p for p in group["params"] if p.requires_grad]
+        dev = ps[0].device
+        step = None
+        for p in ps:
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] += 1
+            step = int(st["step"]) if step is None else step
+        if getattr(self, "_hyper_dev", None) is None:
+            self._hyper_dev = torch.zeros(3, dtype=torch.float32, device=dev)
+            self._hyper_ring = torch.zeros((64, 3), dtype=torch.float32).pin_memory()
+            self._hyper_slot = 0
+        b1, b2 = group["betas"]
+        out = (C.c_float * 3)()
+        _lib.check(_lib.load().lcrec_adam_hyper(float(group["lr"]), float(b1), float(b2), float(group["weight_decay"]), step, out))
+        slot = self._hyper_ring[self._hyper_slot % 64]
+        self._hyper_slot += 1
+        slot[0], slot[1], slot[2] = out[0], out[1], out[2]
+        self._hyper_dev.copy_(slot, non_blocking=True)
+
     @torch.no_grad()
-    def clip_and_step(self, max_norm: float = 0.0, want_norm: bool = False):
+    def clip_and_step(self, max_norm: float = 0.0, want_norm: bool = False, device_hyper: bool = False):
         """Gradient clipping to ``max_norm`` (<= 0: none) over ALL parameter groups (like ``clip_grad_norm_`` on
         ``model.parameters()``) followed by the update.  Returns the total gradient norm (a device tensor) if asked."""
         self._opt_called = True          # what the step wrapper of an LR scheduler records (its call-order warning)
@@ -65,18 +97,30 @@ class FusedAdam(torch.optim.Optimizer):
                 if not ps:
                     continue
                 steps = set()
-                for p in ps:
-                    st = self.state[p]
-                    st["step"] += 1                              # a CPU scalar tensor, as torch.optim keeps it
-                    steps.add(int(st["step"]))
-                if len(steps) != 1:
-                    raise RuntimeError("FusedAdam: parameters of one group must share the step count")
+                if not device_hyper:
+                    for p in ps:
+                        st = self.state[p]
+                        st["step"] += 1                              # a CPU scalar tensor, as torch.optim keeps it
+                        steps.add(int(st["step"]))
+                    if len(steps) != 1:
+                        raise RuntimeError("FusedAdam: parameters of one group must share the step count")
                 n = len(ps)
                 numel = (C.c_int64 * n)(*[p.numel() for p in ps])
                 ws_bytes = int(lib.lcrec_adam_workspace_bytes(n, numel))
                 if getattr(self, "_ws", None) is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
                     self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 b1, b2 = group["betas"]
+                if device_hyper:                                  # scalars of this step were published by prepare_hyper()
+                    _lib.check(lib.lcrec_adam_clip_step_dev(
+                        n, _lib.ptr_array([p.data_ptr() for p in ps]), _lib.ptr_array([p.grad.data_ptr() for p in ps]),
+                        _lib.ptr_array([self.state[p]["exp_avg"].data_ptr() for p in ps]),
+                        _lib.ptr_array([self.state[p]["exp_avg_sq"].data_ptr() for p in ps]), numel,
+                        C.c_void_p(self._hyper_dev.data_ptr()), float(b1), float(b2), float(group["eps"]),
+                        float(group["weight_decay"]), int(bool(group.get("decoupled_weight_decay", True))), float(max_norm), 1,
+                        C.c_void_p(0 if norm_out is None else norm_out.data_ptr()), C.c_void_p(self._ws.data_ptr()),
+                        self._ws.numel(), stream))
+                    _bump_versions(ps)
+                    continue
                 _lib.check(lib.lcrec_adam_clip_step(
                     n, _lib.ptr_array([p.data_ptr() for p in ps]), _lib.ptr_array([p.grad.data_ptr() for p in ps]),
                     _lib.ptr_array([self.state[p]["exp_avg"].data_ptr() for p in ps]),

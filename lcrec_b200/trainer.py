@@ -25,6 +25,8 @@ from .utils import delete_file, ensure_dir, get_local_time, set_color
 
 # Adam / AdamW through lcrec_adam_clip_step (LCREC_FUSED_OPTIM=0: torch.optim + clip_grad_norm_)
 FUSED_OPTIM = os.environ.get("LCREC_FUSED_OPTIM", "1") != "0"
+# the whole step captured in a CUDA graph per batch size (LCREC_TRAIN_GRAPH=0: eager launches, as in round 1)
+TRAIN_GRAPH = os.environ.get("LCREC_TRAIN_GRAPH", "1") != "0"
 
 
 def _linear_warmup_decay(optimizer, warmup, total):
@@ -102,11 +104,42 @@ class Trainer(object):
     def _model_forward(self, data):
         return self.model(data)                              # trainer.py:114
 
+    def _graphed_step(self):
+        """The CUDA-graph form of the step (lcrec_b200.train_graph), or None when this configuration keeps the eager loop:
+        LCREC_TRAIN_GRAPH=0, a CPU device, an optimiser other than the fused Adam / AdamW, a subclass with its own forward
+        plumbing (index_improve's EMA / reset steps read the host), active Dropout, cumulative-average BatchNorm."""
+        if getattr(self, "_gstep", None) is not None:
+            return self._gstep
+        if getattr(self, "_gstep_checked", False):
+            return None
+        self._gstep_checked = True
+        ok = (TRAIN_GRAPH and self.device.type == "cuda" and isinstance(self.optimizer, FusedAdam) and type(self) is Trainer
+              and len(self.optimizer.param_groups) == 1
+              and not any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in self.model.modules())
+              and not any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.momentum is None for m in self.model.modules()))
+        if ok:
+            from .train_graph import GraphedTrainStep
+            self._gstep = GraphedTrainStep(self.model, self.optimizer, forward_fn=self._model_forward, max_norm=1.0)
+            return self._gstep
+        return None
+
     def _train_epoch(self, train_data, epoch_idx):
         self.model.train()
         total_loss = 0
         total_recon_loss = 0
         bar = tqdm(train_data, total=len(train_data), ncols=100, desc=set_color(f"Train {epoch_idx}", "pink"))
+        gstep = self._graphed_step()
+        if gstep is not None:
+            totals = [0.0, 0.0]
+
+            def sink(loss, recon):
+                totals[0] += loss
+                totals[1] += recon
+            for data in bar:
+                gstep.step(data, self.device, sink)       # trainer.py:112-119 as one graph launch
+                self.scheduler.step()
+            gstep.flush(sink)
+            return totals[0], totals[1]
         for data in bar:
             data = data.to(self.device)
             # the two status words the reference reads on the host inside the forward pass (vq.py:59, :81-82) are read at

@@ -1,0 +1,137 @@
+"""Training-path pieces added in round 2 (B200 only): training-mode BatchNorm1d + ReLU kernels, reconstruction-loss kernels,
+the device-scalar Adam step, the CUDA-graph form of the whole step, and the reference Trainer's loss trajectory at the
+run.sh shape (BASELINE configs[1]) with and without BatchNorm (`tests/golden/trainer_c2_steps.npz`, unmodified reference)."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from lcrec_b200.synth import seeded_weights, synth_items
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from lcrec_b200 import ops
+    from lcrec_b200.models import RQVAE
+    from lcrec_b200.models.layers import _BnReluFn
+    from lcrec_b200.optim import FusedAdam
+    import lcrec_b200.trainer as TR
+    DEV = torch.device("cuda:0")
+
+DIMS = [4096, 2048, 1024, 512, 256, 128, 64, 32]
+
+
+@pytest.mark.parametrize("n,c", [(1024, 2048), (424, 64), (37, 100), (2, 32), (3000, 512)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_relu_training_matches_torch(n, c, relu):
+    """Forward values, running statistics and all three gradients of BatchNorm1d(train) [+ ReLU] (layers.py:25-29)."""
+    g = torch.Generator(device=DEV).manual_seed(n + c)
+    y = (torch.randn(n, c, device=DEV, generator=g) * 1.7 + 0.3)
+    gy = torch.randn(n, c, device=DEV, generator=g)
+    ref = torch.nn.BatchNorm1d(c).to(DEV).train()
+    ref.weight.data = torch.rand(c, device=DEV, generator=g) + 0.5
+    ref.bias.data = torch.randn(c, device=DEV, generator=g) * 0.1
+    ours = torch.nn.BatchNorm1d(c).to(DEV).train()
+    ours.load_state_dict(ref.state_dict())
+    for step in range(2):                                       # two steps: the running statistics move twice
+        y1 = y.clone().requires_grad_(True)
+        o1 = ref(y1)
+        o1 = torch.relu(o1) if relu else o1
+        o1.backward(gy)
+        y2 = y.clone().requires_grad_(True)
+        ours.zero_grad(); ref_g = (ref.weight.grad.clone(), ref.bias.grad.clone()); ref.zero_grad()
+        o2 = _BnReluFn.apply(y2, ours.weight, ours.bias, ours, relu)
+        o2.backward(gy)
+        np.testing.assert_allclose(o2.detach().cpu().numpy(), o1.detach().cpu().numpy(), rtol=1e-5, atol=2e-6)
+        scale = float(y1.grad.abs().max()) + 1e-30
+        assert float((y2.grad - y1.grad).abs().max()) <= 2e-5 * scale
+        np.testing.assert_allclose(ours.weight.grad.cpu().numpy(), ref_g[0].cpu().numpy(), rtol=2e-5, atol=2e-5 * float(ref_g[0].abs().max()))
+        np.testing.assert_allclose(ours.bias.grad.cpu().numpy(), ref_g[1].cpu().numpy(), rtol=2e-5, atol=2e-5 * float(ref_g[1].abs().max()))
+        np.testing.assert_allclose(ours.running_mean.cpu().numpy(), ref.running_mean.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ours.running_var.cpu().numpy(), ref.running_var.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        assert int(ours.num_batches_tracked) == int(ref.num_batches_tracked) == step + 1
+
+
+@pytest.mark.parametrize("shape", [(1024, 4096), (424, 4096), (7, 13), (1, 1)])
+@pytest.mark.parametrize("kind", ["mse", "l1"])
+def test_recon_loss_matches_torch(shape, kind):
+    g = torch.Generator(device=DEV).manual_seed(shape[0])
+    out = torch.randn(*shape, device=DEV, generator=g, requires_grad=True)
+    x = torch.randn(*shape, device=DEV, generator=g)
+    fn = torch.nn.functional.mse_loss if kind == "mse" else torch.nn.functional.l1_loss
+    ref = fn(out, x)
+    (gref,) = torch.autograd.grad(ref * 0.7, out)
+    loss = ops.recon_loss(out.detach(), x, kind)
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-6)
+    grad = ops.recon_loss_backward(out.detach(), x, kind, torch.tensor(0.7, device=DEV))
+    np.testing.assert_allclose(grad.cpu().numpy(), gref.cpu().numpy(), rtol=1e-6, atol=1e-12)
+
+
+def _c2_model(bn, g):
+    ws, bs, cbs = seeded_weights(DIMS, [256] * 4, 32, seed=int(g["seed_w"]), cb_scale=float(g["cb_scale"]))
+    wd, bd, _ = seeded_weights(DIMS[::-1], [256] * 4, 32, seed=int(g["seed_wd"]))
+    m = RQVAE(in_dim=4096, num_emb_list=[256] * 4, e_dim=32, layers=DIMS[1:-1], bn=bn, kmeans_init=False,
+              sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50)
+    sd = m.state_dict()
+    stride = 4 if bn else 3
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        sd[f"encoder.mlp_layers.{1 + stride * i}.weight"] = torch.from_numpy(w); sd[f"encoder.mlp_layers.{1 + stride * i}.bias"] = torch.from_numpy(b)
+    for i, (w, b) in enumerate(zip(wd, bd)):
+        sd[f"decoder.mlp_layers.{1 + stride * i}.weight"] = torch.from_numpy(w); sd[f"decoder.mlp_layers.{1 + stride * i}.bias"] = torch.from_numpy(b)
+    for l, cb in enumerate(cbs):
+        sd[f"rq.vq_layers.{l}.embedding.weight"] = torch.from_numpy(cb)
+    m.load_state_dict(sd)
+    return m
+
+
+def _c2_args(tmp, steps, bn):
+    return argparse.Namespace(lr=1e-3, epochs=steps, batch_size=1024, num_workers=0, eval_step=50, learner="AdamW",
+                              lr_scheduler_type="linear", warmup_epochs=2, data_path="", weight_decay=1e-4, dropout_prob=0.0, bn=bn,
+                              loss_type="mse", kmeans_init=False, kmeans_iters=10, sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50,
+                              device="cuda:0", num_emb_list=[256] * 4, e_dim=32, quant_loss_weight=1.0, beta=0.25,
+                              layers=DIMS[1:-1], save_limit=5, ckpt_dir=str(tmp))
+
+
+@pytest.mark.parametrize("bn", [False, True])
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_matches_reference_at_run_sh_shape(golden, tmp_path, bn, graph, monkeypatch):
+    """Per-step (total, recon) losses of the unmodified reference Trainer._train_epoch (index/trainer.py:98-125), 6 steps of
+    batch 1024 at the run.sh architecture: step 1 is a pure forward (1e-5), the later ones carry the optimiser updates."""
+    g = golden("trainer_c2_steps")
+    steps, batch = int(g["steps"]), int(g["batch"])
+    x = synth_items(steps * batch, 4096, n_parents=steps * batch // 8, seed=int(g["seed_x"]))
+    monkeypatch.setattr(TR, "TRAIN_GRAPH", graph)
+    tr = TR.Trainer(_c2_args(tmp_path, steps, bn), _c2_model(bn, g), 1)
+    got = []
+    for s in range(steps):
+        got.append(tr._train_epoch([torch.from_numpy(x[s * batch:(s + 1) * batch])], s))
+    got = np.array(got)
+    want = g["losses_bn" if bn else "losses"]
+    print(f"\n[c2 bn={bn} graph={graph}] max rel diff per step {np.abs(got / want - 1).max(axis=1)}")
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-5)
+    np.testing.assert_allclose(got, want, rtol=2e-4)
+    if graph:
+        assert tr._gstep is not None and tr._gstep.capture_error is None and tr._gstep.replays == steps - tr._gstep.warmup
+
+
+def test_graphed_step_equals_eager_step(tmp_path, monkeypatch):
+    """Same model, same batches: the replayed graph and the eager launches are the same kernels in the same order, so the
+    loss trajectory and the final parameters are IDENTICAL (bitwise), over two batch sizes and an LR schedule."""
+    g = {"seed_w": 5, "seed_wd": 6, "cb_scale": 0.3}
+    x = synth_items(5 * 1024, 4096, n_parents=640, seed=9)
+    loaders = [[torch.from_numpy(x[i * 1024:(i + 1) * 1024]) for i in range(4)] + [torch.from_numpy(x[4096:4096 + 424])]] * 3
+    res = []
+    for graph in (False, True):
+        monkeypatch.setattr(TR, "TRAIN_GRAPH", graph)
+        args = _c2_args(tmp_path, 3, False)
+        args.warmup_epochs = 1
+        tr = TR.Trainer(args, _c2_model(False, g), 5)
+        losses = [tr._train_epoch(ld, ep) for ep, ld in enumerate(loaders)]
+        coll = tr._valid_epoch(loaders[0])
+        res.append((np.array(losses), [p.detach().clone() for p in tr.model.parameters()], coll, tr))
+    assert res[1][3]._gstep.capture_error is None and res[1][3]._gstep.replays == 15 - 2 * 3
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+    assert res[0][2] == res[1][2]            # evaluation after graph replays sees the replayed weights (version bump)
