@@ -210,6 +210,15 @@ int lcrec_sinkhorn_dense(const double* distances, int64_t n_rows, int n_codes, d
  * ranks' symmetric buffers (lcrec_sinkhorn_dist_symmetric_bytes each, zeroed once); epoch = steps published on these
  * buffers so far: 0 for the first call, then EXACTLY the previous call's epoch + its iters + 1 (the double-buffered slots
  * alternate on the absolute step, so consecutive calls may overlap without a barrier in between).  Collective: every rank calls it with its own rows.  Workspace as lcrec_sinkhorn_workspace_bytes. */
+/* argmax per row of sinkhorn_algorithm(distances, epsilon, iters) - all that vq.py:83 consumes in the training forward - as ONE
+ * thread-block cluster (<= 16 CTAs): exp(-d / eps) in shared memory, column marginals exchanged through distributed shared memory
+ * with a cluster barrier per iteration; scaling-vector iterations + the reference's last column step evaluated literally (exact
+ * ties as in layers.py:85-108).  Falls back to lcrec_sinkhorn_dense (scratch plan in ws) when the problem does not fit
+ * (n_rows / 16 x n_codes doubles > 200 KB), iters == 0, or lcrec_sinkhorn_set_dense_cluster(0). */
+int64_t lcrec_sinkhorn_dense_argmax_workspace_bytes(int64_t n_rows, int n_codes);
+int lcrec_sinkhorn_dense_argmax(const double* distances, int64_t n_rows, int n_codes, double epsilon, int iters,
+                                int64_t* argmax, int32_t* flags, void* ws, int64_t ws_bytes, void* stream);
+int lcrec_sinkhorn_set_dense_cluster(int on);
 int64_t lcrec_sinkhorn_dist_symmetric_bytes(int n_codes);
 int lcrec_sinkhorn_dense_dist(const double* distances, int64_t n_rows_local, int64_t n_rows_global, int n_codes,
                               double epsilon, int iters, double* q, int64_t* argmax, int32_t* flags,

@@ -67,7 +67,7 @@ class VectorQuantizer(nn.Module):
             _, idx, flags = self.dist_sinkhorn(dc, self.sk_epsilon, self.sk_iters)
         else:
             dc = ops.center_distances(d)                              # fp64, raises AssertionError like vq.py:59
-            _, idx, flags = ops.sinkhorn_dense(dc, self.sk_epsilon, self.sk_iters, want_argmax=True)
+            idx, flags = ops.sinkhorn_dense_argmax(dc, self.sk_epsilon, self.sk_iters)     # cluster / DSMEM kernel
         ops.check_later("sinkhorn", flags)                            # peer-arrival error; NaN/Inf print of vq.py:81-82
         return idx
 

@@ -604,6 +604,27 @@ def sinkhorn_dense(distances: torch.Tensor, epsilon: float, iters: int, want_arg
     return (q, arg, flags) if want_argmax else q
 
 
+def sinkhorn_dense_argmax(distances: torch.Tensor, epsilon: float, iters: int):
+    """``argmax(sinkhorn_algorithm(distances, epsilon, iters), -1)`` (vq.py:78-83) without materialising the plan: one
+    thread-block cluster with the kernel matrix in distributed shared memory (lcrec_sinkhorn_dense_argmax).
+    Returns (indices int64 (B,), flags int32 (1,))."""
+    _need_cuda(distances)
+    lib = _lib.load()
+    d = distances.detach().to(torch.float64).contiguous()
+    b, k = d.shape
+    arg = torch.empty((b,), dtype=torch.int64, device=d.device)
+    flags = torch.zeros(1, dtype=torch.int32, device=d.device)
+    ws = _ws(lib.lcrec_sinkhorn_dense_argmax_workspace_bytes(b, k), d.device)
+    with torch.cuda.device(d.device):
+        _lib.check(lib.lcrec_sinkhorn_dense_argmax(_p(d), b, k, float(epsilon), int(iters), _p(arg), _p(flags), _p(ws), ws.numel(),
+                                                   _stream(d)))
+    return arg, flags
+
+
+def sinkhorn_set_dense_cluster(on: bool) -> None:
+    _lib.check(_lib.load().lcrec_sinkhorn_set_dense_cluster(int(bool(on))))
+
+
 def collisions(codes: torch.Tensor, n_codes: Sequence[int]):
     """Sort/unique over packed code tuples -> CSR collision groups + counts (generate_indices.py:18-42)."""
     _need_cuda(codes)

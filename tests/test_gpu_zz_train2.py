@@ -135,3 +135,36 @@ def test_graphed_step_equals_eager_step(tmp_path, monkeypatch):
     for a, b in zip(res[0][1], res[1][1]):
         assert torch.equal(a, b)
     assert res[0][2] == res[1][2]            # evaluation after graph replays sees the replayed weights (version bump)
+
+
+@pytest.mark.parametrize("b,k,eps", [(1024, 256, 0.003), (424, 256, 0.003), (512, 32, 0.003), (37, 100, 0.05), (1, 256, 0.003),
+                                     (33, 256, 0.003), (1600, 256, 0.01), (3000, 256, 0.003), (1024, 1024, 0.003)])
+def test_dense_cluster_argmax_equals_literal_kernel(b, k, eps):
+    """The cluster / DSMEM Sinkhorn of the training forward (scaling vectors + literal last column step) picks the same code
+    as the literal cooperative kernel on every row - including rows decided by exact ties (duplicated rows) - and falls back
+    to it when the problem does not fit one cluster's shared memory (3000 x 256, 1024 x 1024)."""
+    g = torch.Generator(device=DEV).manual_seed(b * 7 + k)
+    lat = torch.randn(b, 32, device=DEV, generator=g) * 0.3
+    cb = torch.randn(k, 32, device=DEV, generator=g) * 0.3
+    if b >= 8:
+        lat[5] = lat[2]; lat[6] = lat[2]                       # exact duplicates: the exact-tie regime of SURVEY F3
+    dc = ops.center_distances(ops.vq_distances(lat, cb))
+    _, want, f0 = ops.sinkhorn_dense(dc, eps, 50, want_argmax=True)
+    got, f1 = ops.sinkhorn_dense_argmax(dc, eps, 50)
+    assert int(f0.item()) == int(f1.item()) == 0
+    assert torch.equal(got, want)
+    try:
+        ops.sinkhorn_set_dense_cluster(False)
+        got2, _ = ops.sinkhorn_dense_argmax(dc, eps, 50)
+    finally:
+        ops.sinkhorn_set_dense_cluster(True)
+    assert torch.equal(got2, want)
+
+
+def test_dense_cluster_argmax_on_reference_golden(golden):
+    """argmax of the reference's own sinkhorn_algorithm outputs (tests/golden/sinkhorn_kat.npz, incl. exact-duplicate rows)."""
+    g = golden("sinkhorn_kat")
+    for ci, (n, k, eps, iters) in enumerate(g["meta"]):
+        dc = torch.from_numpy(g[f"dc_{ci}"]).to(DEV).double()
+        got, _ = ops.sinkhorn_dense_argmax(dc, float(eps), int(iters))
+        assert np.array_equal(got.cpu().numpy(), g[f"arg_{ci}"]), ci
