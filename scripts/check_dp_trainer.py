@@ -1,7 +1,7 @@
 """torchrun --nproc-per-node N scripts/check_dp_trainer.py : data-parallel training (lcrec_b200.dp_trainer) against the loss
 trajectory of the UNMODIFIED single-device reference Trainer (tests/golden/trainer_steps.npz: 4 epochs x 4 batches of 256,
 AdamW + linear warm-up + clip 1.0, Sinkhorn on the last level) from the same initial state, and the step time of
-BASELINE configs[1] (global batch 1024) on N GPUs.  Prints one JSON line.  NOT YET RUN (round 1 ended without GPU budget)."""
+BASELINE configs[1] (global batch 1024) on N GPUs.  Prints one JSON line."""
 import argparse, json, os, sys, tempfile, time
 import numpy as np
 import torch, torch.distributed as dist
@@ -41,6 +41,33 @@ lo, hi = sync.clone(), sync.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 replicas_equal = bool(torch.equal(lo, hi))
 
+# ---- the run.sh shape against the UNMODIFIED reference Trainer's per-step losses (tests/golden/trainer_c2_steps.npz), bn False and
+# True: under DP the BatchNorm kernels all-reduce their per-channel sums (synchronised BN = the single-device global batch)
+from lcrec_b200.synth import seeded_weights, synth_items
+g2 = dict(np.load(os.path.join(root, "tests", "golden", "trainer_c2_steps.npz")))
+D = [4096, 2048, 1024, 512, 256, 128, 64, 32]
+c2 = {}
+for bn in (False, True):
+    ws, bs, cbs = seeded_weights(D, [256] * 4, 32, seed=int(g2["seed_w"]), cb_scale=float(g2["cb_scale"]))
+    wd, bd, _ = seeded_weights(D[::-1], [256] * 4, 32, seed=int(g2["seed_wd"]))
+    mm = RQVAE(in_dim=4096, num_emb_list=[256] * 4, e_dim=32, layers=D[1:-1], bn=bn, kmeans_init=False, sk_epsilons=[0.0, 0.0, 0.0, 0.003], sk_iters=50)
+    sd = mm.state_dict()
+    stride = 4 if bn else 3
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        sd[f"encoder.mlp_layers.{1 + stride * i}.weight"] = torch.from_numpy(w); sd[f"encoder.mlp_layers.{1 + stride * i}.bias"] = torch.from_numpy(b)
+    for i, (w, b) in enumerate(zip(wd, bd)):
+        sd[f"decoder.mlp_layers.{1 + stride * i}.weight"] = torch.from_numpy(w); sd[f"decoder.mlp_layers.{1 + stride * i}.bias"] = torch.from_numpy(b)
+    for l, cb in enumerate(cbs):
+        sd[f"rq.vq_layers.{l}.embedding.weight"] = torch.from_numpy(cb)
+    mm.load_state_dict(sd)
+    steps, batch = int(g2["steps"]), int(g2["batch"])
+    xx = synth_items(steps * batch, 4096, n_parents=steps * batch // 8, seed=int(g2["seed_x"]))
+    trc = DataParallelTrainer(make_args(layers=D[1:-1], num_emb_list=[256] * 4, e_dim=32, epochs=steps, warmup_epochs=2, bn=bn, batch_size=batch), mm, 1)
+    got = np.array([trc._train_epoch([torch.from_numpy(xx[s * batch:(s + 1) * batch])], s) for s in range(steps)])
+    want = g2["losses_bn" if bn else "losses"]
+    c2["bn" if bn else "plain"] = {"first_step_rel": float(np.abs(got[0] / want[0] - 1).max()), "max_rel": float(np.abs(got / want - 1).max())}
+    del trc, mm
+
 # ---- step time at the run.sh shape, global batch 1024
 dims = [2048, 1024, 512, 256, 128, 64]
 args2 = make_args(layers=dims, num_emb_list=[256] * 4, e_dim=32, epochs=1)
@@ -55,7 +82,9 @@ tr2._train_epoch(loader2, 1)
 torch.cuda.synchronize(); dist.barrier()
 ms = (time.perf_counter() - t0) / len(loader2) * 1e3
 if rank == 0:
-    print(json.dumps({"world": world, "max_rel_dev_from_reference_losses": rel, "ok": bool(rel < 2e-3 and replicas_equal),
+    print(json.dumps({"world": world, "max_rel_dev_from_reference_losses": rel,
+                      "ok": bool(rel < 2e-3 and replicas_equal and all(v["first_step_rel"] < 2e-5 and v["max_rel"] < 5e-4 for v in c2.values())),
+                      "run_sh_shape_vs_reference_trainer": c2,
                       "collision_rate": coll, "reference_collision_rate": float(g["collision_rate"]), "replicas_equal": replicas_equal,
                       "ms_per_step_global_batch_1024": ms, "items_per_s": 1024 / ms * 1e3}))
 dist.barrier()

@@ -110,7 +110,11 @@ def test_trainer_matches_reference_at_run_sh_shape(golden, tmp_path, bn, graph, 
     want = g["losses_bn" if bn else "losses"]
     print(f"\n[c2 bn={bn} graph={graph}] max rel diff per step {np.abs(got / want - 1).max(axis=1)}")
     np.testing.assert_allclose(got[0], want[0], rtol=1e-5)
-    np.testing.assert_allclose(got, want, rtol=2e-4)
+    # later steps: 2e-4, or 4x what the UNMODIFIED reference differs from itself by when only its BLAS thread count changes
+    # (recorded in the fixture: with BatchNorm the trajectory is chaotic - 1e-5 at step 3, 7e-4 at step 4, 8e-3 at step 6)
+    noise = g["self_noise_bn" if bn else "self_noise"]
+    for s in range(steps):
+        np.testing.assert_allclose(got[s], want[s], rtol=max(2e-4, 4.0 * float(noise[s])), err_msg=f"step {s + 1}")
     if graph:
         assert tr._gstep is not None and tr._gstep.capture_error is None and tr._gstep.replays == steps - tr._gstep.warmup
 
