@@ -43,6 +43,7 @@ SIGNATURES = {
     "lcrec_sinkhorn_dense_argmax_workspace_bytes": (i64, [i64, C.c_int]),
     "lcrec_sinkhorn_dense_argmax": (C.c_int, [vp, i64, C.c_int, f64, C.c_int, vp, vp, vp, i64, vp]),
     "lcrec_sinkhorn_set_dense_cluster": (C.c_int, [C.c_int]),
+    "lcrec_sinkhorn_set_wide": (C.c_int, [C.c_int]),
     "lcrec_sinkhorn_dist_symmetric_bytes": (i64, [C.c_int]),
     "lcrec_sinkhorn_dense_dist": (C.c_int, [vp, i64, i64, C.c_int, f64, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_uint64,
                                             vp, i64, vp]),

@@ -621,6 +621,11 @@ def sinkhorn_dense_argmax(distances: torch.Tensor, epsilon: float, iters: int):
     return arg, flags
 
 
+def sinkhorn_set_wide(on: bool) -> None:
+    """Large-codebook path of the per-group Sinkhorn (batched distances + one cluster per group); False = CTA kernel only."""
+    _lib.check(_lib.load().lcrec_sinkhorn_set_wide(int(bool(on))))
+
+
 def sinkhorn_set_dense_cluster(on: bool) -> None:
     _lib.check(_lib.load().lcrec_sinkhorn_set_dense_cluster(int(bool(on))))
 

@@ -65,7 +65,10 @@ for bn in (False, True):
     trc = DataParallelTrainer(make_args(layers=D[1:-1], num_emb_list=[256] * 4, e_dim=32, epochs=steps, warmup_epochs=2, bn=bn, batch_size=batch), mm, 1)
     got = np.array([trc._train_epoch([torch.from_numpy(xx[s * batch:(s + 1) * batch])], s) for s in range(steps)])
     want = g2["losses_bn" if bn else "losses"]
-    c2["bn" if bn else "plain"] = {"first_step_rel": float(np.abs(got[0] / want[0] - 1).max()), "max_rel": float(np.abs(got / want - 1).max())}
+    noise = g2["self_noise_bn" if bn else "self_noise"]          # the reference against itself with another BLAS thread count
+    per_step = np.abs(got / want - 1).max(axis=1)
+    c2["bn" if bn else "plain"] = {"first_step_rel": float(per_step[0]), "max_rel": float(per_step.max()),
+                                   "within_4x_reference_self_noise": bool((per_step <= np.maximum(2e-4, 4.0 * noise)).all())}
     del trc, mm
 
 # ---- step time at the run.sh shape, global batch 1024
@@ -83,7 +86,7 @@ torch.cuda.synchronize(); dist.barrier()
 ms = (time.perf_counter() - t0) / len(loader2) * 1e3
 if rank == 0:
     print(json.dumps({"world": world, "max_rel_dev_from_reference_losses": rel,
-                      "ok": bool(rel < 2e-3 and replicas_equal and all(v["first_step_rel"] < 2e-5 and v["max_rel"] < 5e-4 for v in c2.values())),
+                      "ok": bool(rel < 2e-3 and replicas_equal and all(v["first_step_rel"] < 2e-5 and v["within_4x_reference_self_noise"] for v in c2.values())),
                       "run_sh_shape_vs_reference_trainer": c2,
                       "collision_rate": coll, "reference_collision_rate": float(g["collision_rate"]), "replicas_equal": replicas_equal,
                       "ms_per_step_global_batch_1024": ms, "items_per_s": 1024 / ms * 1e3}))

@@ -350,6 +350,43 @@ def test_sinkhorn_groups_large_codebook_match_oracle(k, d):
     assert near <= max(2, n_items // 100), (near, n_items)
 
 
+@pytest.mark.parametrize("k,d", [(8192, 256), (2048, 64), (4096, 128)])
+@pytest.mark.parametrize("mode", [2, 1])
+def test_sinkhorn_wide_path_is_exact(k, d, mode):
+    """Large codebooks on the cluster path (csrc/sinkhorn_wide.cuh: batched fma-chain distances + one cluster of 1 / 2 / 4 / 8
+    CTAs per group): the picks equal the oracle evaluated in the kernels' summation order on EVERY row (groups of 2 ... 24 rows
+    on the clusters, 25 and 40 rows on the CTA kernel), and equal the CTA-kernel-only path."""
+    rng = np.random.default_rng(k + d + mode)
+    sizes = np.array([2, 3, 2, 4, 6, 7, 12, 13, 24, 25, 40, 2, 3, 5, 9, 2, 2, 3, 16, 8, 3, 2])
+    n_items = int(sizes.sum())
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    centres = (rng.standard_normal((len(sizes), d)) * 0.05).astype(np.float32)
+    resid = np.repeat(centres, sizes, axis=0) + (rng.standard_normal((n_items, d)) * 0.01).astype(np.float32)
+    resid[off[3] + 1] = resid[off[3]]                    # exact duplicates inside a group: the exact-tie regime (SURVEY F3)
+    cb = (rng.standard_normal((k, d)) * 0.05).astype(np.float32)
+    mem = rng.permutation(n_items + 7)[:n_items].astype(np.int64)          # members are not the identity
+    rows_all = np.zeros((n_items + 7, d), np.float32)
+    rows_all[mem] = resid
+    out = {}
+    try:
+        ops.sinkhorn_set_mode(mode)
+        for wide in (True, False):
+            ops.sinkhorn_set_wide(wide)
+            codes = torch.zeros((n_items + 7, 4), dtype=torch.int64, device=DEV)
+            fl = ops.sinkhorn_groups(T(rows_all), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV), len(sizes), n_items,
+                                     0.003, 50, codes, 3)
+            assert fl == 0
+            out[wide] = codes.cpu().numpy()[:, 3]
+    finally:
+        ops.sinkhorn_set_mode(2)
+        ops.sinkhorn_set_wide(True)
+    assert np.array_equal(out[True], out[False])
+    for g in range(len(sizes)):
+        rows = mem[off[g]:off[g + 1]]
+        want = O.vq_assign(rows_all[rows], cb, True, 0.003, 50, order="chain")
+        assert np.array_equal(out[True][rows], want), (g, sizes[g])
+
+
 # ------------------------------------------------------------------ a12/a14: collisions
 @pytest.mark.parametrize("n,k,L", [(0, 16, 3), (1, 16, 3), (5, 4, 2), (10000, 16, 3), (100000, 256, 4), (70000, 8192, 4),
                                    (4097, 65536, 4)])
