@@ -630,14 +630,15 @@ def run_c2(a):
             for ep in range(warmup):
                 tr._train_epoch(loader, ep)
             torch.cuda.synchronize()
-            n0 = ops.launch_count()
+            n0 = ops.launch_count() + (tr._gstep.replayed_launches if getattr(tr, "_gstep", None) is not None else 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for ep in range(steps):
                 losses = tr._train_epoch(loader, warmup + ep)
             e1.record()
             torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps, ops.launch_count() - n0, losses
+        n1 = ops.launch_count() + (tr._gstep.replayed_launches if getattr(tr, "_gstep", None) is not None else 0)
+        return e0.elapsed_time(e1) / steps, n1 - n0, losses
 
     tr = build(a.bn)
     # untimed: the step of every batch size runs eagerly 3 times and is then captured; the batch of 424 occurs once per epoch,

@@ -395,6 +395,24 @@ int lcrec_masked_mean_pool(const void* hidden, int dtype, const int64_t* mask, i
 int64_t lcrec_index_json_workspace_bytes(int64_t n);
 int lcrec_index_json(const int64_t* codes, int64_t n, int n_levels, char* out, int64_t out_cap, int64_t* total_bytes_dev,
                      void* ws, int64_t ws_bytes, void* stream);
+/* ---- (e) multi-GPU hand-over of PASS-0 results to the owners of the prefix buckets (lcrec_b200/distributed.py) -----------
+ * pack: owner = hash(first L-1 codes) mod world; STABLE partition of this rank's n items by owner straight into `send` =
+ * `world` slabs of lcrec_exchange_slab_bytes(slab_rows, L, D) bytes: [16 B header: int64 row count, int64 overflow flag][records:
+ * L int64 codes + D fp32 residual, lcrec_exchange_record_bytes each]; slot[i] = owner * slab_rows + position (-1: slab overflow).
+ * ONE equal-split all-to-all moves the slabs.  unpack: received slabs -> (rows x L) codes + (rows x D) residuals in source-rank
+ * order (= ascending global item id for contiguous shards).  pack_last / scatter_last: the resolved last-level codes travel back
+ * in (world x slab_rows) int64 slabs along the same routes and land in the origin's table through slot[]. */
+int64_t lcrec_exchange_record_bytes(int n_levels, int e_dim);
+int64_t lcrec_exchange_slab_bytes(int64_t slab_rows, int n_levels, int e_dim);
+int64_t lcrec_exchange_workspace_bytes(int64_t n, int world);
+int lcrec_exchange_pack(const int64_t* codes, const float* resid, int64_t n, int n_levels, int e_dim, const int32_t* n_codes,
+                        int world, int64_t slab_rows, void* send, int32_t* slot, int64_t* counts_dev, void* ws, int64_t ws_bytes,
+                        void* stream);
+int lcrec_exchange_unpack(const void* recv, int world, int64_t slab_rows, int n_levels, int e_dim, int64_t* codes, float* resid,
+                          int64_t cap_rows, void* stream);
+int lcrec_exchange_pack_last(const int64_t* codes, int n_levels, const void* recv, int world, int64_t slab_rows, int e_dim,
+                             int64_t* back, int64_t n_rows_hint, void* stream);
+int lcrec_exchange_scatter_last(const int64_t* back_recv, const int32_t* slot, int64_t n, int n_levels, int64_t* codes, void* stream);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).
  * Tags: 0 = operand split of the input, 1+l = MLP layer l, 17 = splits of the tail layers, 20 = fused RQ,
  * 21 = collision checks, 22 / 23 = per-group Sinkhorn of the first / the later rounds.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */

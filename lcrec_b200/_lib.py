@@ -106,6 +106,13 @@ SIGNATURES = {
     "lcrec_recon_loss_backward": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, vp]),
     "lcrec_index_json_workspace_bytes": (i64, [i64]),
     "lcrec_index_json": (C.c_int, [vp, i64, C.c_int, vp, i64, vp, vp, i64, vp]),
+    "lcrec_exchange_record_bytes": (i64, [C.c_int, C.c_int]),
+    "lcrec_exchange_slab_bytes": (i64, [i64, C.c_int, C.c_int]),
+    "lcrec_exchange_workspace_bytes": (i64, [i64, C.c_int]),
+    "lcrec_exchange_pack": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, C.POINTER(i32), C.c_int, i64, vp, vp, vp, vp, i64, vp]),
+    "lcrec_exchange_unpack": (C.c_int, [vp, C.c_int, i64, C.c_int, C.c_int, vp, vp, i64, vp]),
+    "lcrec_exchange_pack_last": (C.c_int, [vp, C.c_int, vp, C.c_int, i64, C.c_int, vp, i64, vp]),
+    "lcrec_exchange_scatter_last": (C.c_int, [vp, vp, i64, C.c_int, vp, vp]),
     "lcrec_kmeanspp_workspace_bytes": (i64, [i64, C.c_int]),
     "lcrec_kmeanspp_seed": (C.c_int, [vp, i64, C.c_int, C.c_int, i64, vp, C.c_int, vp, vp, vp, i64, vp]),
     "lcrec_indexer_codes": (vp, [vp]),

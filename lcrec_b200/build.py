@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblcrec_b200.so")
-SOURCES = ["abi.cu", "linear_tf32x3.cu", "linear_pair.cu", "rq_fused.cu", "sinkhorn.cu", "collide.cu", "ema.cu", "pool.cu", "kmeans.cu", "rq_train.cu", "optim.cu", "kmeanspp.cu", "train_extra.cu", "json_emit.cu", "sinkhorn_cluster.cu"]
+SOURCES = ["abi.cu", "linear_tf32x3.cu", "linear_pair.cu", "rq_fused.cu", "sinkhorn.cu", "collide.cu", "ema.cu", "pool.cu", "kmeans.cu", "rq_train.cu", "optim.cu", "kmeanspp.cu", "train_extra.cu", "json_emit.cu", "sinkhorn_cluster.cu", "exchange.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -104,6 +104,69 @@ class CudaBackend:
             raise RuntimeError(f"sinkhorn_groups failed with flags {flags}")
 
 
+class NativeExchange:
+    """The hand-over of PASS-0 results to the bucket owners and back as native kernels + TWO equal-split all-to-alls
+    (csrc/exchange.cu): owner hash + stable partition + record packing in one pass over the items, fixed-size slabs per
+    destination (25 % slack over the even share; a header carries the row count), so no split sizes cross the host and the only
+    host read is the 8 x 8-byte count vector the owner needs to size its table."""
+
+    def __init__(self, backend, n_local_max: int, world: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.C = C
+        self.backend, self.world, self.group = backend, int(world), group
+        self.L, self.D = len(backend.cbs), int(backend.cbs[0].shape[1])
+        self.n_codes = _lib.i32_array(backend.n_codes)
+        dev = backend.cbs[0].device
+        self.dev = dev
+        self.slab_rows = int(n_local_max / world * 1.25) + 4096
+        self.slab_bytes = int(self.lib.lcrec_exchange_slab_bytes(self.slab_rows, self.L, self.D))
+        self.send = torch.empty(self.slab_bytes * world, dtype=torch.uint8, device=dev)
+        self.recv = torch.empty_like(self.send)
+        self.back_send = torch.empty((world, self.slab_rows), dtype=torch.int64, device=dev)
+        self.back_recv = torch.empty_like(self.back_send)
+        self.slot = torch.empty(max(n_local_max, 1), dtype=torch.int32, device=dev)
+        self.ws = torch.empty(int(self.lib.lcrec_exchange_workspace_bytes(max(n_local_max, 1), world)), dtype=torch.uint8, device=dev)
+        self.cap = world * self.slab_rows
+        self.sub_codes = torch.empty((self.cap, self.L), dtype=torch.int64, device=dev)
+        self.sub_resid = torch.empty((self.cap, self.D), dtype=torch.float32, device=dev)
+
+    def _st(self):
+        return self.C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def forward(self, codes_local: torch.Tensor, resid_local: torch.Tensor):
+        """-> (sub_codes view, sub_resid view) of the rows this rank owns, in ascending global item order."""
+        from . import _lib
+        from .ops import _p
+        n = int(codes_local.shape[0])
+        assert n <= self.slot.numel()
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.lcrec_exchange_pack(_p(codes_local), _p(resid_local), n, self.L, self.D, self.n_codes, self.world,
+                                                    self.slab_rows, _p(self.send), _p(self.slot), None, _p(self.ws), self.ws.numel(), self._st()))
+            dist.all_to_all_single(self.recv, self.send, group=self.group)
+            hdr = self.recv.view(self.world, self.slab_bytes)[:, :16].contiguous().view(torch.int64).cpu()      # the one host read
+            if int(hdr[:, 1].sum()) != 0:
+                raise RuntimeError("prefix-bucket exchange: a destination slab overflowed (bucket skew beyond 25 %); "
+                                   "set LCREC_EXCHANGE=generic for the split-size path")
+            n_mine = int(hdr[:, 0].sum())
+            _lib.check(self.lib.lcrec_exchange_unpack(_p(self.recv), self.world, self.slab_rows, self.L, self.D, _p(self.sub_codes),
+                                                      _p(self.sub_resid), n_mine, self._st()))
+        return self.sub_codes[:n_mine], self.sub_resid[:n_mine]
+
+    def backward(self, sub_codes: torch.Tensor, codes_local: torch.Tensor) -> torch.Tensor:
+        """Resolved last-level codes back to their origin; returns the origin's table (a copy of codes_local, last column updated)."""
+        from . import _lib
+        from .ops import _p
+        out = codes_local.clone()
+        with torch.cuda.device(self.dev):
+            _lib.check(self.lib.lcrec_exchange_pack_last(_p(sub_codes), self.L, _p(self.recv), self.world, self.slab_rows, self.D,
+                                                         _p(self.back_send), int(sub_codes.shape[0]), self._st()))
+            dist.all_to_all_single(self.back_recv, self.back_send, group=self.group)
+            _lib.check(self.lib.lcrec_exchange_scatter_last(_p(self.back_recv), _p(self.slot), int(out.shape[0]), self.L, _p(out), self._st()))
+        return out
+
+
 def bucket_owner(codes: torch.Tensor, n_codes, world: int) -> torch.Tensor:
     """Owner rank of every item's prefix bucket: the mixed-radix value of the first L-1 codes, mixed with a
     multiplicative hash (so that skewed code usage still spreads evenly), modulo world."""
@@ -164,6 +227,34 @@ def generate_codes_sharded(backend, x_local: torch.Tensor, plan: ShardPlan, rank
     # shards are contiguous blocks and the send order inside a shard is ascending.
     world = plan.world
     last = codes_local.shape[1] - 1
+    import os as _os
+    if codes_local.is_cuda and hasattr(backend, "indexer") and _os.environ.get("LCREC_EXCHANGE", "native") == "native" and world <= 16:
+        ex = getattr(backend, "_native_exchange", None)
+        if ex is None or ex.world != world or ex.slot.numel() < codes_local.shape[0] or getattr(backend, "_native_exchange_group", None) is not group:
+            ex = backend._native_exchange = NativeExchange(backend, max(plan.max_count, int(codes_local.shape[0])), world, group)
+            backend._native_exchange_group = group
+        sub_codes, sub_resid = ex.forward(codes_local.contiguous(), resid_local.contiguous())
+        mark("partition+exchange")
+        st = resolve_rounds(backend, sub_codes, sub_resid, max_rounds)
+        mark("rounds")
+        out = ex.backward(sub_codes, codes_local)
+        n_mine = int(sub_codes.shape[0])
+        agg = torch.tensor([st["n_unique"], st["groups_round1"], st["rows_round1"], st["sinkhorn_rows"], st["rounds"], st["max_multiplicity"]],
+                           dtype=torch.int64, device=codes_local.device)
+        gathered = torch.empty((world, 6), dtype=torch.int64, device=codes_local.device)
+        dist.all_gather_into_tensor(gathered, agg.view(1, 6), group=group)         # one collective for all statistics
+        gl = gathered.cpu()
+        n_unique, g1, r1, rows = [int(v) for v in gl[:, :4].sum(0).tolist()]
+        rounds, max_mult = [int(v) for v in gl[:, 4:].max(0).values.tolist()]
+        mark("return+stats")
+        if timing and rank == 0:
+            torch.cuda.synchronize()
+            import sys
+            print("dist timing (ms): " + ", ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.2f}" for a, b in zip(marks[:-1], marks[1:])), file=sys.stderr)
+        stats = {"rounds": rounds, "n_unique": n_unique, "groups_round1": g1, "rows_round1": r1, "sinkhorn_rows": rows,
+                 "max_multiplicity": max_mult, "collision_rate": (plan.n_total - n_unique) / max(plan.n_total, 1),
+                 "bucket_items_this_rank": n_mine}
+        return out, stats
     owner = bucket_owner(codes_local, n_codes, world)
     order = torch.argsort(owner, stable=True)                      # items grouped by destination, ascending inside
     send_counts = torch.bincount(owner, minlength=world)

@@ -34,6 +34,7 @@ class _Entry:
         self.x: Optional[torch.Tensor] = None
         self.report: Optional[torch.Tensor] = None
         self.kinds: List[str] = []
+        self.n_launches = 0                  # kernels of liblcrec_b200.so recorded in the graph
 
 
 class GraphedTrainStep:
@@ -46,6 +47,7 @@ class GraphedTrainStep:
         self.entries: Dict[int, _Entry] = {}
         self.capture_error: Optional[str] = None if enabled else "disabled"
         self.replays = self.eager_steps = 0
+        self.replayed_launches = 0           # library kernels executed through graph replays (the library's own counter only sees eager launches)
         self._ring = None
         self._slot = 0
         self._pending = []                              # (event, pinned row, kinds) of steps whose report is in flight
@@ -116,8 +118,10 @@ class GraphedTrainStep:
                 try:
                     torch.cuda.synchronize(device)
                     g = torch.cuda.CUDAGraph()
+                    before = ops.launch_count()
                     with torch.cuda.graph(g):
                         e.report, e.kinds = self._run(e.x)
+                    e.n_launches = ops.launch_count() - before
                     e.graph = g
                 except Exception as exc:  # noqa: BLE001 - fall back to the eager step, loudly
                     self.capture_error = f"{type(exc).__name__}: {exc}"
@@ -135,6 +139,7 @@ class GraphedTrainStep:
             e.graph.replay()
             _bump_versions(self._versioned)        # the replay rewrote parameters / running statistics behind torch's back
             self.replays += 1
+            self.replayed_launches += e.n_launches
             report, kinds = e.report, e.kinds
         self._publish(report, kinds)
         self._collect(1, sink)
