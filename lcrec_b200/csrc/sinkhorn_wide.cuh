@@ -149,9 +149,10 @@ struct SkWideArgs {
   double eps; int iters; int64_t* codes; int n_levels; int level; int32_t* flags;
   int32_t* risky_list; int* risky_count;       // null: no certainty filter (mode 1)
   int rows_cap_cta;                            // rows of E that fit this CTA's shared memory
+  int rows_lo, rows_hi;                        // groups outside [rows_lo, rows_hi] are skipped
 };
 
-template <int C>
+template <int C, bool LIT>
 __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const SkWideArgs a) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char wd_smem[];
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
     const int64_t g = a.list[w];
     const int64_t beg = a.offsets[g];
     const int n = (int)(a.offsets[g + 1] - beg);
+    if (n < a.rows_lo || n > a.rows_hi) continue;        // (a list that mixes sizes, e.g. the literal re-run of risky groups)
     const double Bd = (double)n;
     // ---- distances of this CTA's columns, max / min over the whole group (vq.py:54-55)
     float lmax = -INFINITY, lmin = INFINITY;
@@ -225,19 +227,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
           E[(size_t)i * Kc + kl] = exp(-((double)dc / a.eps));
         }
       }
-    double v[kWideCpt];
-#pragma unroll
-    for (int c = 0; c < kWideCpt; ++c) v[c] = 1.0;
-    // ---- scaling-vector iterations
-    for (int it = 0; it < a.iters; ++it) {
-      for (int i = 0; i < n; ++i) {                      // row partials: thread chain over its columns, then the warp tree
-        double rs = 0.0;
-#pragma unroll
-        for (int c = 0; c < kWideCpt; ++c) {
-          const int kl = tid + kWideThreads * c;
-          if (c < ncols && kl < Kc) rs = fma(E[(size_t)i * Kc + kl], v[c], rs);
-        }
-        rs = warp_sum(rs);
+    // Row totals of all CTAs: thread partials part[i] (i < n) -> warp tree -> shared memory -> (C > 1) DSMEM exchange.
+    // RCP: u_s[i] = 1 / (B total_i) (scaling form); otherwise u_s[i] = total_i (literal form).
+    auto reduce_rows = [&](const double* part, bool rcp) {
+      for (int i = 0; i < n; ++i) {
+        const double rs = warp_sum(part[i]);
         if (lane == 0) red[warp * kWideMaxRows + i] = rs;
       }
       __syncthreads();
@@ -246,7 +240,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
         rs = warp_sum(rs);
         if (lane == 0) {
           if constexpr (C > 1) xch[(parity & 1) * kWideMaxRows + warp] = rs;
-          else u_s[warp] = fast_rcp(Bd * rs);
+          else u_s[warp] = rcp ? fast_rcp(Bd * rs) : rs;
         }
       }
       if constexpr (C > 1) {
@@ -254,38 +248,167 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
         if (tid < n) {
           double rs = 0.0;
           for (unsigned r = 0; r < (unsigned)C; ++r) rs += cluster.map_shared_rank(xch, r)[(parity & 1) * kWideMaxRows + tid];   // rank order
-          u_s[tid] = fast_rcp(Bd * rs);
+          u_s[tid] = rcp ? fast_rcp(Bd * rs) : rs;
         }
         ++parity;
       }
       __syncthreads();
-      if (it == a.iters - 1) break;
+    };
+    double part[kWideMaxRows];
+    if constexpr (LIT) {
+      // ---- the reference's literal in-place divide sequence (layers.py:93-107) on this cluster's copy of the matrix
+      double tot = 0.0;
+      for (int i = 0; i < n; ++i)
 #pragma unroll
-      for (int c = 0; c < kWideCpt; ++c) {               // column step, local to the CTA
+        for (int c = 0; c < kWideCpt; ++c) {
+          const int kl = tid + kWideThreads * c;
+          if (c < ncols && kl < Kc) tot += E[(size_t)i * Kc + kl];
+        }
+      part[0] = tot;
+      {                                                  // grand total through the same reduction (one "row")
+        const double rs = warp_sum(part[0]);
+        if (lane == 0) red[warp * kWideMaxRows] = rs;
+        __syncthreads();
+        if (warp == 0) {
+          double t = warp_sum(red[lane * kWideMaxRows]);
+          if (lane == 0) { if constexpr (C > 1) xch[(parity & 1) * kWideMaxRows] = t; else u_s[0] = t; }
+        }
+        if constexpr (C > 1) {
+          cluster.sync();
+          if (tid == 0) {
+            double t = 0.0;
+            for (unsigned r = 0; r < (unsigned)C; ++r) t += cluster.map_shared_rank(xch, r)[(parity & 1) * kWideMaxRows];
+            u_s[0] = t;
+          }
+          ++parity;
+        }
+        __syncthreads();
+      }
+      const double total = u_s[0];
+      __syncthreads();
+      for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int c = 0; c < kWideCpt; ++c) {
+          const int kl = tid + kWideThreads * c;
+          if (c < ncols && kl < Kc) E[(size_t)i * Kc + kl] /= total;                        // layers.py:94
+        }
+      for (int it = 0; it < a.iters; ++it) {
+        for (int i = 0; i < n; ++i) {
+          double rs = 0.0;
+#pragma unroll
+          for (int c = 0; c < kWideCpt; ++c) {
+            const int kl = tid + kWideThreads * c;
+            if (c < ncols && kl < Kc) rs += E[(size_t)i * Kc + kl];
+          }
+          part[i] = rs;
+        }
+        reduce_rows(part, false);
+#pragma unroll
+        for (int c = 0; c < kWideCpt; ++c) {
+          const int kl = tid + kWideThreads * c;
+          if (c < ncols && kl < Kc) {
+            double cs = 0.0;
+            for (int i = 0; i < n; ++i) {                                                    // rows: /= rowsum, /= B (layers.py:99-100)
+              const double q = (E[(size_t)i * Kc + kl] / u_s[i]) / Bd;
+              E[(size_t)i * Kc + kl] = q;
+              cs += q;
+            }
+            for (int i = 0; i < n; ++i) E[(size_t)i * Kc + kl] = (E[(size_t)i * Kc + kl] / cs) / Kd;      // columns (layers.py:103-104)
+          }
+        }
+        __syncthreads();
+      }
+      for (int i = 0; i < n; ++i)
+#pragma unroll
+        for (int c = 0; c < kWideCpt; ++c) {
+          const int kl = tid + kWideThreads * c;
+          if (c < ncols && kl < Kc) {
+            const double val = E[(size_t)i * Kc + kl] * Bd;                                  // layers.py:107
+            bad = bad || isnan(val) || isinf(val);
+            E[(size_t)i * Kc + kl] = val;
+          }
+        }
+    } else {
+      // ---- scaling-vector iterations.  R_1 with v = 1, then (iters - 1) FUSED passes [column step with u_k; row partials with
+      // the new v_k]: one read of the thread's columns per iteration instead of two (the kernel is shared-memory-bandwidth
+      // bound: 8 doubles x n rows per thread per read).  NRR rows of a column are held in registers inside a pass.
+      constexpr int NRR = C == 1 ? 3 : (C == 2 ? 6 : 0);
+      double v[kWideCpt];
+#pragma unroll
+      for (int c = 0; c < kWideCpt; ++c) v[c] = 1.0;
+      for (int i = 0; i < n; ++i) {
+        double rs = 0.0;
+#pragma unroll
+        for (int c = 0; c < kWideCpt; ++c) {
+          const int kl = tid + kWideThreads * c;
+          if (c < ncols && kl < Kc) rs += E[(size_t)i * Kc + kl];                            // fma(E, 1.0, rs)
+        }
+        part[i] = rs;
+      }
+      reduce_rows(part, true);
+      for (int it = 1; it < a.iters; ++it) {
+        if constexpr (NRR > 0) {
+          double pr[NRR];                                 // row partials of this pass, in registers
+#pragma unroll
+          for (int i = 0; i < NRR; ++i) pr[i] = 0.0;
+#pragma unroll
+          for (int c = 0; c < kWideCpt; ++c) {
+            const int kl = tid + kWideThreads * c;
+            if (c < ncols && kl < Kc) {
+              double e[NRR];
+#pragma unroll
+              for (int i = 0; i < NRR; ++i) e[i] = i < n ? E[(size_t)i * Kc + kl] : 0.0;
+              double cs = 0.0;
+#pragma unroll
+              for (int i = 0; i < NRR; ++i) if (i < n) cs = fma(u_s[i], e[i], cs);
+              const double vc = fast_rcp(Kd * cs);
+              v[c] = vc;
+#pragma unroll
+              for (int i = 0; i < NRR; ++i) if (i < n) pr[i] = fma(e[i], vc, pr[i]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NRR; ++i) if (i < n) part[i] = pr[i];
+        } else {
+#pragma unroll
+          for (int c = 0; c < kWideCpt; ++c) {            // column step (local), v in registers
+            const int kl = tid + kWideThreads * c;
+            if (c < ncols && kl < Kc) {
+              double cs = 0.0;
+              for (int i = 0; i < n; ++i) cs = fma(u_s[i], E[(size_t)i * Kc + kl], cs);
+              v[c] = fast_rcp(Kd * cs);
+            }
+          }
+          for (int i = 0; i < n; ++i) {                   // row partials with the new v
+            double rs = 0.0;
+#pragma unroll
+            for (int c = 0; c < kWideCpt; ++c) {
+              const int kl = tid + kWideThreads * c;
+              if (c < ncols && kl < Kc) rs = fma(E[(size_t)i * Kc + kl], v[c], rs);
+            }
+            part[i] = rs;
+          }
+        }
+        __syncthreads();                                 // every thread has read u_s before reduce_rows overwrites it
+        reduce_rows(part, true);
+      }
+      // ---- literal last column step on the materialised plan, * B (rounded products, plain adds, IEEE divisions)
+#pragma unroll
+      for (int c = 0; c < kWideCpt; ++c) {
         const int kl = tid + kWideThreads * c;
         if (c < ncols && kl < Kc) {
           double cs = 0.0;
-          for (int i = 0; i < n; ++i) cs = fma(u_s[i], E[(size_t)i * Kc + kl], cs);
-          v[c] = fast_rcp(Kd * cs);
+          for (int i = 0; i < n; ++i) cs = __dadd_rn(cs, __dmul_rn(__dmul_rn(u_s[i], E[(size_t)i * Kc + kl]), v[c]));
+          for (int i = 0; i < n; ++i) {
+            const double q = __dmul_rn(__dmul_rn(u_s[i], E[(size_t)i * Kc + kl]), v[c]);
+            const double val = __dmul_rn(__ddiv_rn(__ddiv_rn(q, cs), Kd), Bd);
+            bad = bad || isnan(val) || isinf(val);
+            E[(size_t)i * Kc + kl] = val;
+          }
         }
       }
     }
-    // ---- literal last column step on the materialised plan, * B (rounded products, plain adds, IEEE divisions)
     const double scale = Kd / Bd;
-#pragma unroll
-    for (int c = 0; c < kWideCpt; ++c) {
-      const int kl = tid + kWideThreads * c;
-      if (c < ncols && kl < Kc) {
-        double cs = 0.0;
-        for (int i = 0; i < n; ++i) cs = __dadd_rn(cs, __dmul_rn(__dmul_rn(u_s[i], E[(size_t)i * Kc + kl]), v[c]));
-        for (int i = 0; i < n; ++i) {
-          const double q = __dmul_rn(__dmul_rn(u_s[i], E[(size_t)i * Kc + kl]), v[c]);
-          const double val = __dmul_rn(__ddiv_rn(__ddiv_rn(q, cs), Kd), Bd);
-          bad = bad || isnan(val) || isinf(val);
-          E[(size_t)i * Kc + kl] = val;
-        }
-      }
-    }
     __syncthreads();
     // ---- argmax per row (vq.py:81-83): thread -> warp -> CTA -> cluster, torch.argmax order (NaN first, then value, then index)
     for (int i = 0; i < n; ++i) {
@@ -330,7 +453,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
       if (rank == 0) a.codes[a.members[beg + tid] * a.n_levels + a.level] = bk;
     }
     __syncthreads();
-    if (a.risky_list != nullptr) {
+    if (!LIT && a.risky_list != nullptr) {
       // certainty filter of sinkhorn.cu: is the argmax provably the one the literal kernel computes?
       bool risky = false;
       for (int i = 0; i < n; ++i) {

@@ -621,9 +621,10 @@ def sinkhorn_dense_argmax(distances: torch.Tensor, epsilon: float, iters: int):
     return arg, flags
 
 
-def sinkhorn_set_wide(on: bool) -> None:
-    """Large-codebook path of the per-group Sinkhorn (batched distances + one cluster per group); False = CTA kernel only."""
-    _lib.check(_lib.load().lcrec_sinkhorn_set_wide(int(bool(on))))
+def sinkhorn_set_wide(on) -> None:
+    """Large-codebook path of the per-group Sinkhorn (batched distances + one cluster per group); False / 0 = CTA kernel only,
+    2 = the cluster path with the literal divide form for every group (cross-check of the re-run kernel)."""
+    _lib.check(_lib.load().lcrec_sinkhorn_set_wide(int(on)))
 
 
 def sinkhorn_set_dense_cluster(on: bool) -> None:

@@ -370,7 +370,7 @@ def test_sinkhorn_wide_path_is_exact(k, d, mode):
     out = {}
     try:
         ops.sinkhorn_set_mode(mode)
-        for wide in (True, False):
+        for wide in (True, False, 2):                  # cluster path, CTA kernel only, cluster path in the literal divide form
             ops.sinkhorn_set_wide(wide)
             codes = torch.zeros((n_items + 7, 4), dtype=torch.int64, device=DEV)
             fl = ops.sinkhorn_groups(T(rows_all), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV), len(sizes), n_items,
@@ -381,6 +381,7 @@ def test_sinkhorn_wide_path_is_exact(k, d, mode):
         ops.sinkhorn_set_mode(2)
         ops.sinkhorn_set_wide(True)
     assert np.array_equal(out[True], out[False])
+    assert np.array_equal(out[True], out[2])
     for g in range(len(sizes)):
         rows = mem[off[g]:off[g + 1]]
         want = O.vq_assign(rows_all[rows], cb, True, 0.003, 50, order="chain")
