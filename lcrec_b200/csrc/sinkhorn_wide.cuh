@@ -6,10 +6,10 @@
 // Two kernels replace it for groups of up to 24 rows:
 //
 //  wide_distances_kernel   fp32 distances of ALL colliding rows in one pass, (rows x K) into the workspace: a register-tiled
-//                          SIMT kernel (64 x 128 tile, 4 x 8 outputs per thread) whose every output is ONE fma chain in
+//                          SIMT kernel (128 x 128 tile, 8 x 8 outputs per thread) whose every output is ONE fma chain in
 //                          ascending dimension - bit-identical to the per-group chains of sinkhorn.cu / rq_fused.cu (a
 //                          tensor-core GEMM would be ~10x faster but changes the last ulps, and a Sinkhorn pick can flip on one
-//                          ulp: DESIGN.md 2.1).  The codebook is read once per 64 rows instead of once per group.
+//                          ulp: DESIGN.md 2.1).  The codebook is read once per 128 rows instead of once per group.
 //  sinkhorn_wide_kernel<C> one thread-block CLUSTER of C in {1, 2, 4, 8} CTAs x 1024 threads per group: CTA r owns K / C
 //                          columns, every thread <= 8 of them; E = exp(-dc / eps) for the CTA's columns sits in its shared
 //                          memory (192 KB / (K / C x 8 B) rows: 3, 6, 12, 24), v in registers.  Row step: thread-local fma
@@ -21,7 +21,7 @@
 
 namespace lcrec {
 
-constexpr int kWdBM = 64, kWdBN = 128, kWdBK = 16, kWdThreads = 256;
+constexpr int kWdBM = 128, kWdBN = 128, kWdBK = 16, kWdThreads = 256;
 
 // cc[k] = sum_d cb[k][d]^2 as an fma chain in ascending d (same chain as everywhere else)
 __global__ void wide_sqnorm_kernel(const float* __restrict__ cb, int K, int D, float* __restrict__ cc) {
@@ -32,47 +32,49 @@ __global__ void wide_sqnorm_kernel(const float* __restrict__ cb, int K, int D, f
   cc[k] = s;
 }
 
-// dist[r][k] = (xx_r + cc_k) - 2 dot(r, k) for the CSR rows r < *n_rows_dev (row r = resid[members[r]]), D % 16 == 0, K % 128 == 0
+// dist[r][k] = (xx_r + cc_k) - 2 dot(r, k) for the CSR rows r < offsets[n_groups] (row r = resid[members[r]]), D % 16 == 0,
+// K % 128 == 0.  128 x 128 tile, 16 x 16 threads, 8 x 8 outputs per thread (64 FMAs per four 128-bit shared-memory loads).
 __global__ void __launch_bounds__(kWdThreads) wide_distances_kernel(const float* __restrict__ resid, const int64_t* __restrict__ members,
                                                                    const int64_t* __restrict__ offsets, const int64_t* __restrict__ n_groups_dev,
                                                                    const float* __restrict__ cb, const float* __restrict__ cc, int K, int D,
                                                                    float* __restrict__ dist, int64_t rows_cap) {
-  __shared__ float As[kWdBK][kWdBM + 4];
-  __shared__ float Bs[kWdBK][kWdBN + 4];
+  __shared__ __align__(16) float As[kWdBK][kWdBM + 4];
+  __shared__ __align__(16) float Bs[kWdBK][kWdBN + 4];
   __shared__ float xx_s[kWdBM];
   const int64_t n_rows = min(offsets[*n_groups_dev], rows_cap);
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads: 8 columns x 4 rows each
+  const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads: rows ty * 8 .. + 7, columns tx * 8 .. + 7
   const int64_t row_tiles = (n_rows + kWdBM - 1) / kWdBM;
   const int col_tiles = K / kWdBN;
   for (int64_t t = blockIdx.x; t < row_tiles * col_tiles; t += gridDim.x) {
     const int64_t r0 = (t / col_tiles) * kWdBM;
     const int c0 = (int)(t % col_tiles) * kWdBN;
-    float acc[4][8];
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float xx = 0.f;                                  // threads 0..63: squared norm of row r0 + tid (chain in ascending d)
+    float xx = 0.f;                                  // threads 0..127: squared norm of row r0 + tid (chain in ascending d)
     const int64_t my_row = r0 + tid;
     const float* xrow = (tid < kWdBM && my_row < n_rows) ? resid + members[my_row] * D : nullptr;
-    // loaders: A tile 64 rows x 16 dims (one float4 per thread), B tile 128 codes x 16 dims (two float4 per thread)
-    const int a_r = tid >> 2, a_d = (tid & 3) * 4;
-    const int64_t a_row = r0 + a_r;
-    const float* a_src = a_row < n_rows ? resid + members[a_row] * D : nullptr;
+    // loaders: 128 rows x 16 dims = 512 float4 per operand, two per thread: row = idx / 4, dims (idx % 4) * 4
+    const float* a_src[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t a_row = r0 + ((tid + h * kWdThreads) >> 2);
+      a_src[h] = a_row < n_rows ? resid + members[a_row] * D : nullptr;
+    }
     for (int d0 = 0; d0 < D; d0 += kWdBK) {
       __syncthreads();
-      {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a_src) v = *reinterpret_cast<const float4*>(a_src + d0 + a_d);
-        As[a_d + 0][a_r] = v.x; As[a_d + 1][a_r] = v.y; As[a_d + 2][a_r] = v.z; As[a_d + 3][a_r] = v.w;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int idx = tid + h * kWdThreads;      // 512 float4: code = idx / 4, dims (idx % 4) * 4
-          const int b_c = idx >> 2, b_d = (idx & 3) * 4;
-          const float4 w = *reinterpret_cast<const float4*>(cb + (size_t)(c0 + b_c) * D + d0 + b_d);
-          Bs[b_d + 0][b_c] = w.x; Bs[b_d + 1][b_c] = w.y; Bs[b_d + 2][b_c] = w.z; Bs[b_d + 3][b_c] = w.w;
-        }
+      for (int h = 0; h < 2; ++h) {
+        const int idx = tid + h * kWdThreads;
+        const int rr = idx >> 2, dd = (idx & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a_src[h]) v = *reinterpret_cast<const float4*>(a_src[h] + d0 + dd);
+        As[dd + 0][rr] = v.x; As[dd + 1][rr] = v.y; As[dd + 2][rr] = v.z; As[dd + 3][rr] = v.w;
+        const float4 w = *reinterpret_cast<const float4*>(cb + (size_t)(c0 + rr) * D + d0 + dd);
+        Bs[dd + 0][rr] = w.x; Bs[dd + 1][rr] = w.y; Bs[dd + 2][rr] = w.z; Bs[dd + 3][rr] = w.w;
       }
       if (xrow)
 #pragma unroll
@@ -80,13 +82,12 @@ __global__ void __launch_bounds__(kWdThreads) wide_distances_kernel(const float*
       __syncthreads();
 #pragma unroll
       for (int dd = 0; dd < kWdBK; ++dd) {             // ascending d: every acc[i][j] is one sequential fma chain
-        float av[4], bv[8];
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[dd][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[dd][ty * 8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[dd][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[dd][tx * 8 + 4]);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = As[dd][ty * 4 + i];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bv[j] = Bs[dd][tx * 8 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
@@ -95,10 +96,10 @@ __global__ void __launch_bounds__(kWdThreads) wide_distances_kernel(const float*
     if (tid < kWdBM) xx_s[tid] = xx;
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t r = r0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = r0 + ty * 8 + i;
       if (r >= n_rows) continue;
-      const float x2 = xx_s[ty * 4 + i];
+      const float x2 = xx_s[ty * 8 + i];
       float out[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) out[j] = (x2 + cc[c0 + tx * 8 + j]) - 2.f * acc[i][j];     // vq.py:71-73 evaluation order
