@@ -347,29 +347,31 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
         part[i] = rs;
       }
       reduce_rows(part, true);
+      const bool rows_in_regs = NRR > 0 && a.rows_hi <= NRR;      // (smaller codebooks give a CTA more rows than NRR: two-read form)
       for (int it = 1; it < a.iters; ++it) {
-        if constexpr (NRR > 0) {
-          double pr[NRR];                                 // row partials of this pass, in registers
+        if (rows_in_regs) {
+          constexpr int NR = NRR > 0 ? NRR : 1;
+          double pr[NR];                                  // row partials of this pass, in registers
 #pragma unroll
-          for (int i = 0; i < NRR; ++i) pr[i] = 0.0;
+          for (int i = 0; i < NR; ++i) pr[i] = 0.0;
 #pragma unroll
           for (int c = 0; c < kWideCpt; ++c) {
             const int kl = tid + kWideThreads * c;
             if (c < ncols && kl < Kc) {
-              double e[NRR];
+              double e[NR];
 #pragma unroll
-              for (int i = 0; i < NRR; ++i) e[i] = i < n ? E[(size_t)i * Kc + kl] : 0.0;
+              for (int i = 0; i < NR; ++i) e[i] = i < n ? E[(size_t)i * Kc + kl] : 0.0;
               double cs = 0.0;
 #pragma unroll
-              for (int i = 0; i < NRR; ++i) if (i < n) cs = fma(u_s[i], e[i], cs);
+              for (int i = 0; i < NR; ++i) if (i < n) cs = fma(u_s[i], e[i], cs);
               const double vc = fast_rcp(Kd * cs);
               v[c] = vc;
 #pragma unroll
-              for (int i = 0; i < NRR; ++i) if (i < n) pr[i] = fma(e[i], vc, pr[i]);
+              for (int i = 0; i < NR; ++i) if (i < n) pr[i] = fma(e[i], vc, pr[i]);
             }
           }
 #pragma unroll
-          for (int i = 0; i < NRR; ++i) if (i < n) part[i] = pr[i];
+          for (int i = 0; i < NR; ++i) if (i < n) part[i] = pr[i];
         } else {
 #pragma unroll
           for (int c = 0; c < kWideCpt; ++c) {            // column step (local), v in registers
