@@ -222,7 +222,9 @@ int lcrec_sinkhorn_set_dense_cluster(int on);
 /* Large codebooks (2048 ... 8192 codes per cluster CTA, e.g. BASELINE configs[4]: 8192 x 256) in lcrec_sinkhorn_groups*: 1 (default) =
  * fp32 distances of ALL colliding rows in one register-tiled pass (each output one fma chain in ascending dimension, as everywhere)
  * + one thread-block cluster of 1 / 2 / 4 / 8 CTAs per group of <= 3 / 6 / 12 / 24 rows with exp(-dc / eps) in shared memory and the
- * row sums exchanged through distributed shared memory; 0 = the CTA kernel for every group (cross-checks). */
+ * row sums exchanged through distributed shared memory (register-resident variants for the classes that hold most groups);
+ * 0 = the CTA kernel for every group, 2 = the cluster path in the literal divide form, 3 = shared-memory cluster kernels only
+ * (cross-checks). */
 int lcrec_sinkhorn_set_wide(int on);
 int64_t lcrec_sinkhorn_dist_symmetric_bytes(int n_codes);
 int lcrec_sinkhorn_dense_dist(const double* distances, int64_t n_rows_local, int64_t n_rows_global, int n_codes,

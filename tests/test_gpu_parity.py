@@ -370,7 +370,7 @@ def test_sinkhorn_wide_path_is_exact(k, d, mode):
     out = {}
     try:
         ops.sinkhorn_set_mode(mode)
-        for wide in (True, False, 2):                  # cluster path, CTA kernel only, cluster path in the literal divide form
+        for wide in (True, False, 2, 3):               # cluster path, CTA kernel only, cluster path literal form / shared-memory kernels only
             ops.sinkhorn_set_wide(wide)
             codes = torch.zeros((n_items + 7, 4), dtype=torch.int64, device=DEV)
             fl = ops.sinkhorn_groups(T(rows_all), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV), len(sizes), n_items,
