@@ -6,13 +6,14 @@
 # Raw pages are exported as CSV next to the reports; profiles/ keeps the CSV summaries.
 set -u
 mkdir -p gpurun_out
-NCU="ncu --set full --clock-control none --import-source on --profile-from-start off"
+NCU="ncu --set full --clock-control none --profile-from-start off"
 $NCU -k regex:linear_pair -c 2 -o gpurun_out/r2_pair_full python bench.py --items 262144 --steps 1 --warmup 1 --no-cpu --no-e2e --profile-window > gpurun_out/r2_pair_full.log 2>&1
 ncu -i gpurun_out/r2_pair_full.ncu-rep --page raw --csv > gpurun_out/r2_pair_full_raw.csv 2>/dev/null
 $NCU -k regex:sinkhorn_dense_cluster -c 1 -o gpurun_out/r2_dense_cluster_full python scripts/probe_train_kernels.py --short > gpurun_out/r2_dense_cluster_full.log 2>&1
 ncu -i gpurun_out/r2_dense_cluster_full.ncu-rep --page raw --csv > gpurun_out/r2_dense_cluster_full_raw.csv 2>/dev/null
 $NCU -k regex:"sinkhorn_wide|wide_distances" -c 6 -o gpurun_out/r2_wide_full python bench.py --config c5 --steps 1 --warmup 1 --no-cpu --no-e2e --profile-window > gpurun_out/r2_wide_full.log 2>&1
 ncu -i gpurun_out/r2_wide_full.ncu-rep --page raw --csv > gpurun_out/r2_wide_full_raw.csv 2>/dev/null
+rm -f gpurun_out/r2_wide_full.ncu-rep        # 55 MB with sources: the pull-back limit is 64 MiB; the raw page is what is kept
 ls -la gpurun_out/*.ncu-rep gpurun_out/*_raw.csv
 # launch list of the default bench command (the driver's), for the share-of-step check
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 2000 --csv --log-file gpurun_out/r2_default_launches.csv \
