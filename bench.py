@@ -459,15 +459,19 @@ def run_gpu_arm(a):
         eng = ("f16 x3, linear_pair_kernel<64,3> (tcgen05 cta_group::2, 256x256 tiles, persistent)" if a.engine == 1
                else "tf32 x3, linear_split3_kernel<256,16,4,false>")
         traffic = None
-        try:   # DRAM bytes of one launch of this kernel from the committed ncu --set full capture (same rows per launch)
-            summ = json.load(open(os.path.join(ROOT, "profiles", "r1_v5_pair_ncu_summary.json")))["layer1"]
-            if a.engine == 1 and summ["rows_per_launch"] == rows_per_launch:
-                traffic = summ["dram_bytes_read"] + summ["dram_bytes_write"]
-        except Exception:  # noqa: BLE001
-            traffic = None
+        traffic_src = None
+        for name in ("r2_pair_ncu_summary.json", "r1_v5_pair_ncu_summary.json"):
+            try:   # DRAM bytes of one launch of this kernel from the committed ncu --set full capture (same rows per launch)
+                summ = json.load(open(os.path.join(ROOT, "profiles", name)))["layer1"]
+                if a.engine == 1 and summ["rows_per_launch"] == rows_per_launch and CONFIG == "c3":
+                    traffic = summ["dram_bytes_read"] + summ["dram_bytes_write"]
+                    traffic_src = name
+                    break
+            except Exception:  # noqa: BLE001
+                traffic = None
         roof = {"bound": "tensor", "kernel": f"{eng} (encoder layer 1, 4096->2048)",
                 "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": (ach / pk["bf16_sustained"]) if ach else None,
-                "traffic": traffic, "traffic_unit": "bytes of DRAM read + write per launch (ncu, profiles/r1_v5_pair_ncu_summary.json); "
+                "traffic": traffic, "traffic_unit": f"bytes of DRAM read + write per launch (ncu --set full, profiles/{traffic_src}); "
                                                     "algorithmic: 2.18 GB operands + 1.07 GB output",
                 "peak_source": pk["source"] + ", bf16 dense sustained",
                 "note": "achieved = algorithmic fp32 GEMM FLOPs (2*M*4096*2048 per launch) / CUDA-event launch time; the kernel issues 3 MMAs "

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
   __shared__ float mm[4];
   __shared__ int misc[1];
   const int K = a.K, Kc = K / C;
+  if (Kc != CP * kWrThreads) return;                    // the host dispatches this kernel only for K = C x CP x 512: every column slot is live
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = C > 1 ? cluster.block_rank() : 0;
   const int n_work = *a.count;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
       for (int c = 0; c < CP; ++c) {
         const int kl = tid + kWrThreads * c;
         E[i][c] = 0.0;
-        if (i < n && kl < Kc) {
+        if (i < n) {
           const float d = a.dist[(beg + i) * K + rank * Kc + kl];
           E[i][c] = (double)d;
           lmax = fmaxf(lmax, d); lmin = fminf(lmin, d);
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
 #pragma unroll
       for (int c = 0; c < CP; ++c) {
         const int kl = tid + kWrThreads * c;
-        if (i < n && kl < Kc) {
+        if (i < n) {
           const float dc = ((float)E[i][c] - mid) / amp;                    // fp32 centring, vq.py:60
           E[i][c] = exp(-((double)dc / a.eps));                             // layers.py:87
         }
@@ -101,6 +102,8 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
           if constexpr (C > 1) xch[parity & 1][warp] = rs;
           else u_s[slot][warp] = fast_rcp(Bd * rs);
         }
+      } else if (warp < RM && lane == 0) {
+        u_s[slot][warp] = 0.0;                           // rows beyond the group: E = 0 and u = 0, the hot loops run unpredicated
       }
       if constexpr (C > 1) {
         cluster.sync();
@@ -108,6 +111,8 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
           double rs = 0.0;
           for (unsigned r = 0; r < (unsigned)C; ++r) rs += cluster.map_shared_rank(&xch[0][0], r)[(parity & 1) * RM + tid];     // rank order
           u_s[slot][tid] = fast_rcp(Bd * rs);
+        } else if (tid < RM) {
+          u_s[slot][tid] = 0.0;
         }
         ++parity;
       }
@@ -124,19 +129,21 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
     int cur = 0;
     reduce_rows(part, cur);
     for (int it = 1; it < a.iters; ++it) {               // fused [column step with u_cur; row partials with the new v]
+      constexpr int UR = RM <= 6 ? RM : 1;               // u in registers for the small classes, broadcast shared-memory reads beyond
+      double u[UR];
+#pragma unroll
+      for (int i = 0; i < UR; ++i) u[i] = u_s[cur][i];
 #pragma unroll
       for (int i = 0; i < RM; ++i) part[i] = 0.0;
+      const double* us = u_s[cur];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        const int kl = tid + kWrThreads * c;
-        if (kl < Kc) {
-          double cs = 0.0;
+      for (int c = 0; c < CP; ++c) {                     // CP independent chains, no predicates: rows beyond n carry E = 0, u = 0
+        double cs = 0.0;
 #pragma unroll
-          for (int i = 0; i < RM; ++i) if (i < n) cs = fma(u_s[cur][i], E[i][c], cs);
-          const double vc = fast_rcp(Kd * cs);
+        for (int i = 0; i < RM; ++i) cs = fma(RM <= 6 ? u[i < UR ? i : 0] : us[i], E[i][c], cs);
+        const double vc = fast_rcp(Kd * cs);
 #pragma unroll
-          for (int i = 0; i < RM; ++i) if (i < n) part[i] = fma(E[i][c], vc, part[i]);
-        }
+        for (int i = 0; i < RM; ++i) part[i] = fma(E[i][c], vc, part[i]);
       }
       reduce_rows(part, cur ^ 1);                        // (its first barrier comes after every thread's reads of u_s[cur])
       cur ^= 1;
@@ -145,8 +152,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
     const double scale = Kd / Bd;
 #pragma unroll
     for (int c = 0; c < CP; ++c) {
-      const int kl = tid + kWrThreads * c;
-      if (kl < Kc) {
+      {
         double vc = 1.0;
         if (a.iters > 1) {
           double cs0 = 0.0;
@@ -174,11 +180,8 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
         double bv = 0.0; int bk = 0x7fffffff;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-          const int kl = tid + kWrThreads * c;
-          if (kl < Kc) {
-            const int k = (int)rank * Kc + kl;
-            if (bk == 0x7fffffff || arg_better(E[i][c], k, bv, bk)) { bv = E[i][c]; bk = k; }
-          }
+          const int k = (int)rank * Kc + tid + kWrThreads * c;
+          if (bk == 0x7fffffff || arg_better(E[i][c], k, bv, bk)) { bv = E[i][c]; bk = k; }
         }
         for (int o = 16; o > 0; o >>= 1) {
           const double ob = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -221,8 +224,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
           if (!(best == best)) risky = true;
 #pragma unroll
           for (int c = 0; c < CP; ++c) {
-            const int kl = tid + kWrThreads * c;
-            if (kl < Kc && (int)rank * Kc + kl != bk) {
+            if ((int)rank * Kc + tid + kWrThreads * c != bk) {
               const double val = E[i][c];
               const double dev = fmax(fmax(0.0, 1.0 - val * scale) + 0x1p-50, rowdev);
               if (dev > 0x1p-40 && val >= best - best * (0x1p-51 + 2e-11 * dev)) risky = true;
