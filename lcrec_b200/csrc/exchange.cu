@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kExThreads) ex_scatter_kernel(const int64_t* _
         unsigned char* rec = send + (size_t)o * slab_bytes + kExHeader + (size_t)dest * rec_bytes;
         int64_t* rc = reinterpret_cast<int64_t*>(rec);
         for (int l = 0; l < L; ++l) rc[l] = codes[i * L + l];
-        float* rr = reinterpret_cast<float*>(rec + (size_t)L * 8);
+        float* rr = reinterpret_cast<float*>(rec + (((size_t)L * 8 + 15) & ~(size_t)15));
         if ((D & 3) == 0) {
           const float4* src = reinterpret_cast<const float4*>(resid + i * D);
           float4* dst = reinterpret_cast<float4*>(rr);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kExThreads) ex_unpack_kernel(const unsigned ch
     const unsigned char* rec = recv + (size_t)s * slab_bytes + kExHeader + (size_t)(r - start[s]) * rec_bytes;
     const int64_t* rc = reinterpret_cast<const int64_t*>(rec);
     for (int l = 0; l < L; ++l) codes[r * L + l] = rc[l];
-    const float* rr = reinterpret_cast<const float*>(rec + (size_t)L * 8);
+    const float* rr = reinterpret_cast<const float*>(rec + (((size_t)L * 8 + 15) & ~(size_t)15));
     if ((D & 3) == 0) {
       const float4* src = reinterpret_cast<const float4*>(rr);
       float4* dst = reinterpret_cast<float4*>(resid + r * D);
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(kExThreads) ex_scatter_last_kernel(const int64
 
 using namespace lcrec;
 
-extern "C" int64_t lcrec_exchange_record_bytes(int n_levels, int e_dim) { return (int64_t)n_levels * 8 + round_up((int64_t)e_dim * 4, 16); }
+// codes padded to 16 bytes so that the residual part of every record is float4-aligned (3 levels: 24 -> 32 bytes)
+extern "C" int64_t lcrec_exchange_record_bytes(int n_levels, int e_dim) { return round_up((int64_t)n_levels * 8, 16) + round_up((int64_t)e_dim * 4, 16); }
 extern "C" int64_t lcrec_exchange_slab_bytes(int64_t slab_rows, int n_levels, int e_dim) {
   return round_up(kExHeader + slab_rows * lcrec_exchange_record_bytes(n_levels, e_dim), 256);
 }
