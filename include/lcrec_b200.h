@@ -152,6 +152,14 @@ int lcrec_adam_clip_step_dev(int n_tensors, float* const* params, float* const* 
                              double eps, double weight_decay, int decoupled, double max_norm, int write_clipped_grads,
                              float* total_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* SGD / Adagrad / RMSprop of index/trainer.py:62-75 (torch.optim defaults: no momentum, lr_decay 0, alpha 0.99, not centred) with
+ * the same fused clipping: kind 1 = SGD (state NULL), 2 = Adagrad (state = `sum`), 3 = RMSprop (state = `square_avg`).
+ * g *= coef; g += wd p; SGD: p -= lr g; Adagrad: sum += g^2, p -= lr g / (sqrt(sum) + eps); RMSprop: sq = alpha sq + (1 - alpha) g^2,
+ * p -= lr g / (sqrt(sq) + eps).  Workspace: lcrec_adam_workspace_bytes. */
+int lcrec_simple_opt_clip_step(int kind, int n_tensors, float* const* params, float* const* grads, float* const* state,
+                               const int64_t* numel, double lr, double weight_decay, double alpha, double eps, double max_norm,
+                               int write_clipped_grads, float* total_norm_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- a2 (training): BatchNorm1d in training mode + the ReLU behind it (index/models/layers.py:25-29; `run.sh --bn False`
  * parses to bn=True, index/main.py:31) -----------------------------------------------------------------------------------
  * y (n_rows, n_channels) fp32 row-major = the Linear output.  Two launches each way with the per-channel fp64 sums in

@@ -95,6 +95,7 @@ SIGNATURES = {
     "lcrec_adam_hyper": (C.c_int, [f64, f64, f64, f64, i64, C.POINTER(C.c_float)]),
     "lcrec_adam_clip_step_dev": (C.c_int, [C.c_int, pp, pp, pp, pp, C.POINTER(i64), vp, f64, f64, f64, f64, C.c_int, f64,
                                            C.c_int, vp, vp, i64, vp]),
+    "lcrec_simple_opt_clip_step": (C.c_int, [C.c_int, C.c_int, pp, pp, pp, C.POINTER(i64), f64, f64, f64, f64, f64, C.c_int, vp, vp, i64, vp]),
     "lcrec_bn_sums_elems": (i64, [C.c_int]),
     "lcrec_bn_splits": (C.c_int, [i64, C.c_int]),
     "lcrec_bn_forward_reduce": (C.c_int, [vp, i64, C.c_int, vp, vp]),

@@ -127,9 +127,124 @@ adam_step_kernel(OptTable t, AdamArgs a, const double* __restrict__ partial, int
   }
 }
 
+// SGD / Adagrad / RMSprop of index/trainer.py:62-75 (torch.optim defaults: no momentum, lr_decay 0, alpha 0.99, not centred) with the
+// same fused clipping prologue.  `s` = the optimiser's one state tensor per parameter: Adagrad's `sum`, RMSprop's `square_avg`
+// (SGD: none).  torch semantics, fp32:  g *= coef;  g += wd p;
+//   SGD:     p -= lr g
+//   Adagrad: sum += g g;  p -= lr g / (sqrt(sum) + eps)
+//   RMSprop: sq = alpha sq + (1 - alpha) g g;  p -= lr g / (sqrt(sq) + eps)
+struct SimpleOptArgs { float lr, weight_decay, alpha, one_minus_alpha, eps, max_norm; int kind, write_grad; };
+
+__global__ void __launch_bounds__(kOptThreads)
+simple_opt_step_kernel(OptTable t, SimpleOptArgs a, const double* __restrict__ partial, int n_partial, int block_offset,
+                       float* __restrict__ total_norm_out) {
+  __shared__ double red[kOptThreads / 32];
+  __shared__ float coef_s;
+  float coef = 1.f;
+  if (a.max_norm > 0.f) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += kOptThreads) s += partial[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kOptThreads / 32; ++w) tot += red[w];
+      const float norm = (float)sqrt(tot);
+      const float c = __fdiv_rn(a.max_norm, __fadd_rn(norm, 1e-6f));
+      coef_s = c < 1.f ? c : 1.f;
+      if (c != c) coef_s = c;
+      if (blockIdx.x == 0 && block_offset == 0 && total_norm_out) *total_norm_out = norm;
+    }
+    __syncthreads();
+    coef = coef_s;
+  }
+  const int ti = opt_find(t, blockIdx.x);
+  const long long base = (long long)(blockIdx.x - t.first_block[ti]) * kOptChunk;
+  const long long end = min(base + (long long)kOptChunk, t.numel[ti]);
+  float* __restrict__ p = t.p[ti];
+  float* __restrict__ g = t.g[ti];
+  float* __restrict__ st = t.m[ti];
+  for (long long i = base + threadIdx.x; i < end; i += kOptThreads) {
+    float gi = g[i];
+    float pi = p[i];
+    if (a.max_norm > 0.f) {
+      gi = __fmul_rn(gi, coef);
+      if (a.write_grad) g[i] = gi;
+    }
+    if (a.weight_decay != 0.f) gi = fmaf(pi, a.weight_decay, gi);            // grad.add(param, alpha=weight_decay)
+    if (a.kind == 1) {
+      pi = fmaf(-a.lr, gi, pi);                                               // param.add_(grad, alpha=-lr)
+    } else if (a.kind == 2) {
+      const float si = fmaf(gi, gi, st[i]);                                   // state_sum.addcmul_(grad, grad, value=1)
+      st[i] = si;
+      pi = fmaf(-a.lr, __fdiv_rn(gi, __fadd_rn(__fsqrt_rn(si), a.eps)), pi);  // addcdiv_(grad, std, value=-clr)
+    } else {
+      const float si = fmaf(__fmul_rn(gi, gi), a.one_minus_alpha, __fmul_rn(st[i], a.alpha));   // mul_(alpha).addcmul_(g, g, 1 - alpha)
+      st[i] = si;
+      pi = fmaf(-a.lr, __fdiv_rn(gi, __fadd_rn(__fsqrt_rn(si), a.eps)), pi);  // addcdiv_(grad, avg, value=-lr)
+    }
+    p[i] = pi;
+  }
+}
+
 }  // namespace lcrec
 
 using namespace lcrec;
+
+// kind: 1 = SGD, 2 = Adagrad (state = sum), 3 = RMSprop (state = square_avg).  Same calling convention as lcrec_adam_clip_step;
+// `state` may be NULL for SGD.  Workspace: lcrec_adam_workspace_bytes.
+extern "C" int lcrec_simple_opt_clip_step(int kind, int n_tensors, float* const* params, float* const* grads, float* const* state,
+                                          const int64_t* numel, double lr, double weight_decay, double alpha, double eps, double max_norm,
+                                          int write_clipped_grads, float* total_norm_out, void* workspace, int64_t workspace_bytes,
+                                          void* stream) {
+  LC_ARG(kind >= 1 && kind <= 3 && n_tensors >= 0);
+  if (n_tensors == 0) return LCREC_OK;
+  LC_ARG(params && grads && numel && (kind == 1 || state));
+  LC_TRY(lcrec_device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks_total = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    LC_ARG(numel[i] >= 0 && (numel[i] == 0 || (params[i] && grads[i] && (kind == 1 || state[i]))));
+    blocks_total += ceil_div(numel[i], kOptChunk);
+  }
+  if (blocks_total == 0) return LCREC_OK;
+  LC_ARG(blocks_total < ((int64_t)1 << 30));
+  Arena ar(workspace, workspace_bytes);
+  double* partial = ar.take<double>(blocks_total);
+  if (!ar.ok()) { set_error("simple_opt_clip_step: workspace too small"); return LCREC_ERR_NOMEM; }
+  SimpleOptArgs a;
+  a.lr = (float)lr; a.weight_decay = (float)weight_decay; a.alpha = (float)alpha; a.one_minus_alpha = (float)(1.0 - alpha);
+  a.eps = (float)eps; a.max_norm = (float)max_norm; a.kind = kind; a.write_grad = write_clipped_grads;
+  for (int pass = max_norm > 0 ? 0 : 1; pass < 2; ++pass) {
+    int64_t block_offset = 0;
+    for (int t0 = 0; t0 < n_tensors;) {
+      OptTable tab = {};
+      int blocks = 0, k = 0;
+      for (; t0 + k < n_tensors && k < kOptTensors; ++k) {
+        tab.p[k] = params[t0 + k]; tab.g[k] = grads[t0 + k]; tab.m[k] = state ? state[t0 + k] : nullptr; tab.v[k] = nullptr;
+        tab.numel[k] = numel[t0 + k];
+        tab.first_block[k] = blocks;
+        blocks += (int)ceil_div(numel[t0 + k], kOptChunk);
+      }
+      tab.first_block[k] = blocks;
+      tab.n = k;
+      if (blocks > 0) {
+        if (pass == 0) {
+          grad_sqsum_kernel<<<blocks, kOptThreads, 0, st>>>(tab, partial + block_offset);
+          LC_LAUNCH_CHECK("grad_sqsum_kernel");
+        } else {
+          simple_opt_step_kernel<<<blocks, kOptThreads, 0, st>>>(tab, a, partial, (int)blocks_total, (int)block_offset, total_norm_out);
+          LC_LAUNCH_CHECK("simple_opt_step_kernel");
+        }
+      }
+      block_offset += blocks;
+      t0 += k;
+    }
+  }
+  return LCREC_OK;
+}
 
 extern "C" int64_t lcrec_adam_workspace_bytes(int n_tensors, const int64_t* numel) {
   int64_t blocks = 0;

@@ -162,7 +162,7 @@ class DataParallelTrainer(Trainer):
                 self._all_reduce_grads()
                 dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)     # the global-batch loss values
                 self._check_nan(stats[0])
-                if isinstance(self.optimizer, FusedAdam):
+                if isinstance(self.optimizer, FusedAdam) or hasattr(self.optimizer, "clip_and_step"):
                     self.optimizer.clip_and_step(1.0)
                 else:
                     torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)

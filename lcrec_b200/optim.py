@@ -139,3 +139,71 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         self.clip_and_step(0.0)
         return loss
+
+
+class FusedSimple(torch.optim.Optimizer):
+    """SGD / Adagrad / RMSprop as the reference's ``_build_optimizer`` constructs them (index/trainer.py:62-75: only ``lr`` and
+    ``weight_decay`` are passed, everything else is the torch.optim default) with ``clip_grad_norm_`` fused in
+    (``lcrec_simple_opt_clip_step``).  State keys follow torch.optim (``sum`` / ``square_avg`` + ``step``), so ``state_dict()``
+    is interchangeable with ``torch.optim.Adagrad`` / ``RMSprop`` / ``SGD`` (no momentum buffer)."""
+    KINDS = {"sgd": 1, "adagrad": 2, "rmsprop": 3}
+
+    def __init__(self, params, kind: str, lr=1e-2, weight_decay=0.0):
+        kind = kind.lower()
+        if kind not in self.KINDS:
+            raise ValueError(f"FusedSimple: unknown optimiser {kind!r}")
+        defaults = dict(lr=lr, weight_decay=weight_decay)
+        if kind == "adagrad":
+            defaults.update(lr_decay=0, eps=1e-10, initial_accumulator_value=0)
+        elif kind == "rmsprop":
+            defaults.update(alpha=0.99, eps=1e-8, momentum=0, centered=False)
+        else:
+            defaults.update(momentum=0, dampening=0, nesterov=False)
+        super().__init__(params, defaults)
+        self.kind = kind
+        self._state_key = {"sgd": None, "adagrad": "sum", "rmsprop": "square_avg"}[kind]
+
+    @torch.no_grad()
+    def clip_and_step(self, max_norm: float = 0.0):
+        self._opt_called = True
+        if len(self.param_groups) != 1:
+            raise RuntimeError("FusedSimple.clip_and_step: one parameter group expected")
+        group = self.param_groups[0]
+        ps = [p for p in group["params"] if p.grad is not None]
+        if not ps:
+            return
+        for p in ps:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
+                raise RuntimeError("FusedSimple: contiguous fp32 CUDA parameters with dense gradients only (no CPU fallback)")
+            if not p.grad.is_contiguous():
+                p.grad = p.grad.contiguous()
+            st = self.state[p]
+            if self._state_key is not None and self._state_key not in st:
+                st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                st[self._state_key] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if "step" in st:
+                st["step"] += 1
+        lib = _lib.load()
+        dev = ps[0].device
+        n = len(ps)
+        numel = (C.c_int64 * n)(*[p.numel() for p in ps])
+        ws_bytes = int(lib.lcrec_adam_workspace_bytes(n, numel))
+        if getattr(self, "_ws", None) is None or self._ws.numel() < ws_bytes or self._ws.device != dev:
+            self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        state = None if self._state_key is None else _lib.ptr_array([self.state[p][self._state_key].data_ptr() for p in ps])
+        with torch.cuda.device(dev):
+            _lib.check(lib.lcrec_simple_opt_clip_step(
+                self.KINDS[self.kind], n, _lib.ptr_array([p.data_ptr() for p in ps]), _lib.ptr_array([p.grad.data_ptr() for p in ps]), state,
+                numel, float(group["lr"]), float(group["weight_decay"]), float(group.get("alpha", 0.99)), float(group.get("eps", 0.0)),
+                float(max_norm), 1, C.c_void_p(0), C.c_void_p(self._ws.data_ptr()), self._ws.numel(),
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        _bump_versions(ps)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.clip_and_step(0.0)
+        return loss

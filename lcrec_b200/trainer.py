@@ -81,6 +81,9 @@ class Trainer(object):
         if name in ("adam", "adamw") and FUSED_OPTIM and self.device.type == "cuda":
             # same update rule and state layout as torch.optim.Adam / AdamW; clipping + step in two launches
             return FusedAdam(params, decoupled=(name == "adamw"), **kw)
+        if name in ("sgd", "adagrad", "rmsprop") and FUSED_OPTIM and self.device.type == "cuda":
+            from .optim import FusedSimple                     # trainer.py:62-75 with clip_grad_norm_ fused in
+            return FusedSimple(params, name, **kw)
         if name in table:
             opt = table[name](params, **kw)
             if name == "adagrad":
@@ -150,7 +153,7 @@ class Trainer(object):
                 loss, loss_recon = self.model.compute_loss(out, rq_loss, xs=data)
                 self._check_nan(loss)
                 loss.backward()
-                if isinstance(self.optimizer, FusedAdam):
+                if isinstance(self.optimizer, FusedAdam) or hasattr(self.optimizer, "clip_and_step"):
                     self.optimizer.clip_and_step(1.0)                      # trainer.py:117-118 in one native call
                 else:
                     torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)

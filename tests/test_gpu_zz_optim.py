@@ -84,3 +84,36 @@ def test_fused_adam_state_dict_exchange_and_scheduler():
         cpu = [torch.zeros(3, requires_grad=True)]
         cpu[0].grad = torch.ones(3)
         FusedAdam(cpu).step()
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adagrad", "rmsprop"])
+@pytest.mark.parametrize("wd,max_norm", [(1e-4, 1.0), (0.0, 0.0)])
+def test_fused_sgd_adagrad_rmsprop_match_torch(kind, wd, max_norm):
+    """clip_grad_norm_ + torch.optim.SGD / Adagrad / RMSprop as index/trainer.py:62-75 builds them (lr + weight_decay only) against
+    lcrec_simple_opt_clip_step over several steps; the optimiser state is interchangeable with torch's."""
+    from lcrec_b200.optim import FusedSimple
+    pa, pb = _params(3), _params(3)
+    ours = FusedSimple(pa, kind, lr=1e-2, weight_decay=wd)
+    ref = {"sgd": torch.optim.SGD, "adagrad": torch.optim.Adagrad, "rmsprop": torch.optim.RMSprop}[kind](pb, lr=1e-2, weight_decay=wd)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    for step in range(4):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, device=DEV, generator=g) * 2.0
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if max_norm > 0:
+            torch.nn.utils.clip_grad_norm_(pb, max_norm)
+        ref.step()
+        ours.clip_and_step(max_norm)
+        for a, b in zip(pa, pb):
+            if a.numel():
+                np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+                if max_norm > 0:
+                    np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    key = {"sgd": None, "adagrad": "sum", "rmsprop": "square_avg"}[kind]
+    if key:
+        for a, b in zip(pa, pb):
+            if a.numel():
+                np.testing.assert_allclose(ours.state[a][key].cpu().numpy(), ref.state[b][key].cpu().numpy(), rtol=1e-5, atol=1e-7)
+        sd = ours.state_dict()
+        ref2 = type(ref)(_params(3), lr=1e-2, weight_decay=wd)
+        ref2.load_state_dict(sd)                                    # torch's optimiser accepts the fused one's state
