@@ -482,6 +482,21 @@ def run_gpu_arm(a):
                 "launches": l1_calls, "avg_launch_ms": l1_ms / max(l1_calls, 1), "rows_per_launch": rows_per_launch,
                 "kernel_share_of_step": l1_ms / a.steps / ms_step,
                 "hbm_frac_end_to_end": value / world * BYTES_PER_ITEM / 1e9 / pk["hbm_gbs"], "stage_ms_per_step": stage_ms}
+        # second roofline: the per-group Sinkhorn of round 1 against the MEASURED fp64 FMA peak.  Algorithmic fp64 work = 2 K FMAs per row
+        # per iteration (25 600 FMAs per row at K = 256, 50 iterations); reciprocals, exp and the literal last step excluded
+        sk = None
+        try:
+            peak64 = ops.fp64_peak_tflops(device)
+            ms22 = prof.get(22, (0.0, 0))[0] / a.steps
+            rows1 = stats["rows_round1"] / (world if world > 1 else 1)
+            ach64 = 2.0 * rows1 * 2 * N_CODES[-1] * SK_ITERS / (ms22 * 1e-3) / 1e12 if ms22 > 0 else None
+            sk = {"bound": "fp64", "kernel": "per-group Sinkhorn, first round (stage 22)", "achieved": ach64, "peak": peak64, "unit": "TFLOP/s",
+                  "frac": (ach64 / peak64) if ach64 else None, "rows_per_rank": rows1, "ms": ms22,
+                  "peak_source": "measured in this run (lcrec_fp64_peak_probe: 8 independent DFMA chains per thread)",
+                  "note": "algorithmic = 2 K FMAs per row per iteration; per iteration a group also needs K + n reciprocals (~5 fp64 ops each: as "
+                          "much work as the FMAs at n = 2), so the pipe is busier than this fraction says"}
+        except Exception as exc:  # noqa: BLE001
+            sk = {"error": str(exc)}
         cpu = None
         torch_cuda = None
         if world == 1 and not a.no_cpu:
@@ -498,7 +513,7 @@ def run_gpu_arm(a):
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (low-rank parents + noise, random-init encoder, k-means-style codebooks)",
                 "config": workload_config(world, n_local, a.steps, a.warmup, a.cpu_sample), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "index_json": json_ms, "sharded_equals_single": sharded_ok, "stats": stats,
+                "roofline": roof, "roofline_sinkhorn": sk, "cpu_baseline": cpu, "reference_torch_cuda": torch_cuda, "index_json": json_ms, "sharded_equals_single": sharded_ok, "stats": stats,
                 "flop_per_item": FLOP_PER_ITEM, "bytes_per_item": BYTES_PER_ITEM,
                 "algorithmic_tflops_end_to_end": value * FLOP_PER_ITEM / 1e12}
         print(json.dumps(line), flush=True)

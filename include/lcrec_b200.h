@@ -423,6 +423,10 @@ int lcrec_exchange_unpack(const void* recv, int world, int64_t slab_rows, int n_
 int lcrec_exchange_pack_last(const int64_t* codes, int n_levels, const void* recv, int world, int64_t slab_rows, int e_dim,
                              int64_t* back, int64_t n_rows_hint, void* stream);
 int lcrec_exchange_scatter_last(const int64_t* back_recv, const int32_t* slot, int64_t n, int n_levels, int64_t* codes, void* stream);
+/* Measured fp64 FMA peak of the device in FLOP/s (8 independent DFMA chains per thread, 148 x 8 CTAs): the denominator of the
+ * fp64-pipe fraction bench.py reports for the per-group Sinkhorn (MEASURED_PEAKS.json carries no fp64 figure).  ws: >= 8 B x SMs x 2048.
+ * Synchronises the stream. */
+int lcrec_fp64_peak_probe(double* flops_out, void* ws, int64_t ws_bytes, void* stream);
 /* Per-stage device timing with CUDA events on the launching stream (bench.py's live roofline).
  * Tags: 0 = operand split of the input, 1+l = MLP layer l, 17 = splits of the tail layers, 20 = fused RQ,
  * 21 = collision checks, 22 / 23 = per-group Sinkhorn of the first / the later rounds.  collect() synchronises and ADDS elapsed ms / call counts (32 each). */

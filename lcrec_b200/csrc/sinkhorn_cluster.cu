@@ -181,3 +181,42 @@ extern "C" int lcrec_sinkhorn_dense_argmax(const double* distances, int64_t n_ro
   char* rest = (char*)q + round_up((int64_t)sizeof(double) * n_rows * n_codes, 256);
   return lcrec_sinkhorn_dense(distances, n_rows, n_codes, epsilon, iters, q, argmax, flags, rest, ws_bytes - (rest - (char*)ws), stream);
 }
+
+// ---- fp64 FMA peak of this GPU, measured: the denominator of the per-group Sinkhorn's pipe fraction (MEASURED_PEAKS.json has no fp64
+// figure).  Every thread runs 8 independent DFMA chains; 148 x 8 CTAs x 256 threads.  Returns FLOP/s through *flops_out (host).
+namespace lcrec {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* __restrict__ out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace lcrec
+
+extern "C" int lcrec_fp64_peak_probe(double* flops_out, void* ws, int64_t ws_bytes, void* stream) {
+  LC_ARG(flops_out != nullptr);
+  LC_TRY(lcrec_device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ctas = num_sms() * 8, iters = 1 << 14;
+  LC_ARG(ws != nullptr && ws_bytes >= (int64_t)sizeof(double) * ctas * 256);
+  cudaEvent_t e0, e1;
+  LC_CUDA(cudaEventCreate(&e0)); LC_CUDA(cudaEventCreate(&e1));
+  dfma_peak_kernel<<<ctas, 256, 0, st>>>((double*)ws, iters, 0.999999, 1e-9);      // warm-up
+  LC_LAUNCH_CHECK("dfma_peak_kernel");
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    LC_CUDA(cudaEventRecord(e0, st));
+    dfma_peak_kernel<<<ctas, 256, 0, st>>>((double*)ws, iters, 0.999999, 1e-9);
+    LC_LAUNCH_CHECK("dfma_peak_kernel");
+    LC_CUDA(cudaEventRecord(e1, st));
+    LC_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    best = ms < best ? ms : best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *flops_out = 2.0 * 8.0 * (double)iters * (double)ctas * 256.0 / ((double)best * 1e-3);
+  return LCREC_OK;
+}

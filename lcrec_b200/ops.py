@@ -55,6 +55,16 @@ def sinkhorn_set_mode(mode: int) -> None:
     _lib.check(_lib.load().lcrec_sinkhorn_set_mode(int(mode)))
 
 
+def fp64_peak_tflops(device=None) -> float:
+    """Measured DFMA peak of the device in TFLOP/s (lcrec_fp64_peak_probe)."""
+    dev = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+    ws = torch.empty(8 * 2048 * 256, dtype=torch.uint8, device=dev)
+    out = C.c_double()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().lcrec_fp64_peak_probe(C.byref(out), _p(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out.value / 1e12
+
+
 def profile_enable(on: bool) -> None:
     _lib.check(_lib.load().lcrec_profile_enable(int(on)))
 
