@@ -172,3 +172,45 @@ def test_dense_cluster_argmax_on_reference_golden(golden):
         dc = torch.from_numpy(g[f"dc_{ci}"]).to(DEV).double()
         got, _ = ops.sinkhorn_dense_argmax(dc, float(eps), int(iters))
         assert np.array_equal(got.cpu().numpy(), g[f"arg_{ci}"]), ci
+
+
+@pytest.mark.parametrize("bn", [False, True])
+def test_eval_after_graph_replays_sees_the_trained_state(tmp_path, bn, monkeypatch):
+    """The graph replays rewrite parameters and BatchNorm running statistics through raw pointers; the eval-mode encoder (one fused
+    handle with BatchNorm folded in, cached by tensor versions) must nevertheless use the CURRENT values: its latents equal an fp64
+    evaluation of the model's own state_dict after training, and so does the NaN guard of trainer.py:93-95 (one step late at most)."""
+    g = {"seed_w": 5, "seed_wd": 6, "cb_scale": 0.3}
+    x = synth_items(4 * 1024, 4096, n_parents=512, seed=9)
+    monkeypatch.setattr(TR, "TRAIN_GRAPH", True)
+    args = _c2_args(tmp_path, 3, bn)
+    args.warmup_epochs = 0
+    tr = TR.Trainer(args, _c2_model(bn, g), 4)
+    loader = [torch.from_numpy(x[i * 1024:(i + 1) * 1024]) for i in range(4)]
+    xb = torch.from_numpy(x[:256]).to(DEV)
+    with torch.no_grad():
+        tr.model.eval()
+        z_before = tr.model.encoder(xb).clone()                 # builds and caches the fused handle before training
+    for ep in range(3):
+        tr._train_epoch(loader, ep)
+    assert tr._gstep.replays >= 8 and tr._gstep.capture_error is None
+    m = tr.model.eval()
+    with torch.no_grad():
+        z = m.encoder(xb)
+        sd = {k: v.double() for k, v in m.state_dict().items()}
+        h = xb.double()
+        stride = 4 if bn else 3
+        for i in range(7):
+            h = h @ sd[f"encoder.mlp_layers.{1 + stride * i}.weight"].t() + sd[f"encoder.mlp_layers.{1 + stride * i}.bias"]
+            if i < 6:
+                if bn:
+                    p = f"encoder.mlp_layers.{2 + stride * i}."
+                    h = (h - sd[p + "running_mean"]) / torch.sqrt(sd[p + "running_var"] + 1e-5) * sd[p + "weight"] + sd[p + "bias"]
+                h = h.clamp_min(0)
+    scale = float(h.abs().max())
+    assert float((z.double() - h).abs().max()) <= 2e-5 * scale
+    assert float((z - z_before).abs().max()) > 1e-3 * scale     # training really moved the encoder
+    # NaN guard: poison a weight, the ValueError of trainer.py:93-95 arrives (at the latest one step after the poisoned one)
+    with torch.no_grad():
+        next(m.parameters()).fill_(float("nan"))
+    with pytest.raises(ValueError, match="Training loss is nan"):
+        tr._train_epoch(loader, 3)
