@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <utility>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>     // header-only in CUDA 12: ranges cost a few ns unless a tool (nsys / ncu --nvtx) is attached
@@ -388,11 +389,20 @@ extern "C" int lcrec_indexer_run_host(lcrec_indexer_t* ix, const float* x_host, 
       LC_CUDA(cudaMalloc((void**)&ix->stage[i], sizeof(float) * ix->chunk_rows * ix->in_dim));
     }
   }
-  // double-buffered H2D on the copy stream, compute on `st`
-  const int64_t nchunks = ceil_div(n, ix->chunk_rows);
+  // double-buffered H2D on the copy stream, compute on `st`.  The copies are the bottleneck (55 GB/s of pinned H2D against ~14 M
+  // items/s of compute), so what is left after the LAST copy lands - that chunk's encoder pass - is pure tail: the last chunk is cut
+  // into quarters (>= 8192 rows each) so that only a quarter of it remains to be encoded when the link goes idle.
+  std::vector<std::pair<int64_t, int64_t>> pieces;
+  for (int64_t s0 = 0; s0 < n; s0 += ix->chunk_rows) {
+    const int64_t m0 = std::min(ix->chunk_rows, n - s0);
+    if (s0 + m0 < n) { pieces.emplace_back(s0, m0); continue; }
+    const int64_t q = std::max<int64_t>(ceil_div(m0, 4), 8192);
+    for (int64_t t = 0; t < m0; t += q) pieces.emplace_back(s0 + t, std::min(q, m0 - t));
+  }
+  const int64_t nchunks = (int64_t)pieces.size();
   for (int64_t c = 0; c < nchunks; ++c) {
     const int b = (int)(c & 1);
-    const int64_t s = c * ix->chunk_rows, m = std::min(ix->chunk_rows, n - s);
+    const int64_t s = pieces[c].first, m = pieces[c].second;
     if (c >= 2) LC_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->ev_consumed[b], 0));
     LC_CUDA(cudaMemcpyAsync(ix->stage[b], x_host + s * ix->in_dim, sizeof(float) * m * ix->in_dim,
                             cudaMemcpyHostToDevice, ix->copy_stream));
