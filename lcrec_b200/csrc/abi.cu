@@ -391,12 +391,13 @@ extern "C" int lcrec_indexer_run_host(lcrec_indexer_t* ix, const float* x_host, 
   }
   // double-buffered H2D on the copy stream, compute on `st`.  The copies are the bottleneck (55 GB/s of pinned H2D against ~14 M
   // items/s of compute), so what is left after the LAST copy lands - that chunk's encoder pass - is pure tail: the last chunk is cut
-  // into quarters (>= 8192 rows each) so that only a quarter of it remains to be encoded when the link goes idle.
+  // into up to four pieces (>= 8192 rows each) so that only a quarter of it remains to be encoded when the link goes idle.
   std::vector<std::pair<int64_t, int64_t>> pieces;
   for (int64_t s0 = 0; s0 < n; s0 += ix->chunk_rows) {
     const int64_t m0 = std::min(ix->chunk_rows, n - s0);
     if (s0 + m0 < n) { pieces.emplace_back(s0, m0); continue; }
-    const int64_t q = std::max<int64_t>(ceil_div(m0, 4), 8192);
+    const int64_t k = std::max<int64_t>(1, std::min<int64_t>(4, m0 / 8192));      // every piece keeps >= 8192 rows: same kernel choices
+    const int64_t q = ceil_div(m0, k);                                            // (tensor-core RQ path from 4096 rows on) as a full chunk
     for (int64_t t = 0; t < m0; t += q) pieces.emplace_back(s0 + t, std::min(q, m0 - t));
   }
   const int64_t nchunks = (int64_t)pieces.size();
