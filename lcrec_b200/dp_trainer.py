@@ -8,9 +8,10 @@ things cross NVLink, as the north star asks:
 * the Sinkhorn level is ONE (global batch x K) problem (``vq.py:77-79``): ``DistributedSinkhorn`` keeps the row steps local
   and all-reduces the column marginals inside the kernel through peer memory (plus one 2-element MAX all-reduce for the
   centring of ``vq.py:54-55``);
-* the gradients: every loss of the step is a mean over batch rows, so rank r back-propagates ``loss_r * n_r / N`` and ONE
-  ``all_reduce(SUM)`` over a flat bucket that holds every gradient (encoder + decoder 89.5 MB, codebooks 128 KB) yields the
-  gradient of the global-batch loss on every rank; clipping and the optimiser step then run identically everywhere
+* the gradients: every loss of the step is a mean over batch rows, so rank r back-propagates ``loss_r * n_r / N`` and
+  ``all_reduce(SUM)`` over a flat buffer that holds every gradient (encoder + decoder 89.5 MB, codebooks 128 KB) yields the
+  gradient of the global-batch loss on every rank - in ~32 MB buckets that start as soon as autograd has produced their
+  gradients (decoder first), overlapping the rest of the backward pass; clipping and the optimiser step then run identically everywhere
   (``lcrec_adam_clip_step``), so the replicas never diverge.
 
 Codebook k-means initialisation (first batch, ``vq.py:67-68``) runs on the full global batch on every rank with the same
@@ -68,26 +69,91 @@ class DataParallelTrainer(Trainer):
                     q.dist_sinkhorn = DistributedSinkhorn(q.n_e, self.device, self.group)
                 self._sinkhorn_levels.append(q)
 
-    # ---- one all-reduce over every gradient
-    def _all_reduce_grads(self):
+    # ---- gradient reduction: flat buffer, buckets reduced WHILE the backward pass is still running
+    BUCKET_ELEMS = 8 * 1024 * 1024        # ~32 MB of fp32 per all-reduce: the decoder's last layer alone, then groups of smaller layers
+
+    def _setup_buckets(self):
+        """One flat fp32 buffer holds every gradient (parameter order); it is cut into buckets of consecutive parameters in the
+        order autograd produces them (REVERSE parameter order: decoder first).  A post-accumulate-grad hook copies each gradient
+        into its slot; when a bucket is complete its all-reduce starts asynchronously - on NCCL's stream, overlapping the rest of
+        the backward pass - strictly in bucket order on every rank, so that the collectives line up even when a rank has no rows
+        and issues them all at the end."""
         params = [p for p in self.model.parameters() if p.requires_grad]
-        if self._flat is None or self._flat_params != [id(p) for p in params]:
-            total = sum(p.numel() for p in params)
-            self._flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-            self._flat_params = [id(p) for p in params]
-        flat, views, off = self._flat, [], 0
+        self._params = params
+        total = sum(p.numel() for p in params)
+        self._flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._views, off = [], 0
+        offs = []
         for p in params:
-            views.append(flat[off: off + p.numel()].view_as(p))
+            offs.append(off)
+            self._views.append(self._flat[off: off + p.numel()].view_as(p))
             off += p.numel()
-        have = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
-        miss = [v for v, p in zip(views, params) if p.grad is None]
-        if have:
-            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
-        for v in miss:                                          # a rank without rows contributes zeros
-            v.zero_()
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-        for p, v in zip(params, views):                         # gradients now live in the bucket (no copy back)
+        self._buckets = []                 # (first param index, last param index) in issue order
+        hi = len(params) - 1
+        while hi >= 0:
+            lo, size = hi, params[hi].numel()
+            while lo > 0 and size + params[lo - 1].numel() <= self.BUCKET_ELEMS:
+                lo -= 1
+                size += params[lo].numel()
+            self._buckets.append((lo, hi))
+            hi = lo - 1
+        self._bucket_of = {}
+        for b, (lo, hi) in enumerate(self._buckets):
+            for i in range(lo, hi + 1):
+                self._bucket_of[i] = b
+        self._offs = offs
+        self._index = {id(p): i for i, p in enumerate(params)}
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+        self._reset_reduce()
+
+    def _reset_reduce(self):
+        self._pending = [hi - lo + 1 for lo, hi in self._buckets]
+        self._have = [False] * len(self._params)
+        self._handles = []
+        self._next_bucket = 0
+        self._reducing = False
+
+    def _bucket_slice(self, b):
+        lo, hi = self._buckets[b]
+        return self._flat[self._offs[lo]: self._offs[hi] + self._params[hi].numel()]
+
+    def _issue_ready(self):
+        while self._next_bucket < len(self._buckets) and self._pending[self._next_bucket] == 0:
+            self._handles.append(dist.all_reduce(self._bucket_slice(self._next_bucket), op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._next_bucket += 1
+
+    def _on_grad(self, p):
+        if not self._reducing:
+            return                                               # (a backward outside the training step, e.g. a user's probe)
+        i = self._index[id(p)]
+        if self._have[i]:
+            return
+        self._views[i].copy_(p.grad)
+        self._have[i] = True
+        self._pending[self._bucket_of[i]] -= 1
+        self._issue_ready()
+
+    def _all_reduce_grads(self):
+        """Finish the step's reduction: parameters that produced no gradient (a rank without rows, an unused parameter) contribute
+        zeros, the remaining buckets are issued in order, and every gradient then lives in the flat buffer (no copy back)."""
+        if getattr(self, "_params", None) is None:
+            self._setup_buckets()
+            self._reducing = True
+            for i, p in enumerate(self._params):                 # the hooks were registered after this step's backward
+                if p.grad is not None:
+                    self._on_grad(p)
+        for i, have in enumerate(self._have):
+            if not have:
+                self._views[i].zero_()
+                self._have[i] = True
+                self._pending[self._bucket_of[i]] -= 1
+        self._issue_ready()
+        for h in self._handles:
+            h.wait()
+        for p, v in zip(self._params, self._views):
             p.grad = v
+        self._reset_reduce()
 
     def _init_codebooks_on_global_batch(self, data):
         """First training batch (vq.py:67-68): every level's k-means runs on the FULL global batch, on every rank, with the
@@ -150,6 +216,7 @@ class DataParallelTrainer(Trainer):
                     bn.lcrec_sync = (self.group, n) if self.device.type == "cuda" else None
             with ops.defer_checks():
                 self.optimizer.zero_grad()
+                self._reducing = getattr(self, "_params", None) is not None      # hooks copy + reduce during this step's backward
                 self._init_codebooks_on_global_batch(data)
                 stats = torch.zeros(2, dtype=torch.float32, device=self.device)
                 if local.shape[0] > 0:
