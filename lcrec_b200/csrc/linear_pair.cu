@@ -296,7 +296,8 @@ linear_pair_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (args.bias) bv = __ldg(reinterpret_cast<const float4*>(args.bias + col_base + j));
         float t0 = acc[j] * cs.x + bv.x, t1 = acc[j + 1] * cs.y + bv.y, t2 = acc[j + 2] * cs.z + bv.z, t3 = acc[j + 3] * cs.w + bv.w;
-        if (args.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); t2 = fmaxf(t2, 0.f); t3 = fmaxf(t3, 0.f); }
+        // ReLU that lets NaN through like torch.relu (fmaxf(NaN, 0) would be 0 and hide a diverged run from trainer.py:93-95)
+        if (args.relu) { t0 = t0 < 0.f ? 0.f : t0; t1 = t1 < 0.f ? 0.f : t1; t2 = t2 < 0.f ? 0.f : t2; t3 = t3 < 0.f ? 0.f : t3; }
         acc[j] = t0; acc[j + 1] = t1; acc[j + 2] = t2; acc[j + 3] = t3;
         amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t0), fabsf(t1))), fmaxf(fabsf(t2), fabsf(t3)));
       }

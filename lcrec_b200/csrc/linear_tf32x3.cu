@@ -224,7 +224,7 @@ linear_split3_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_c
           float t = acc[j + i];
           if constexpr (F16) { if (col + i < args.n_out) t = (t * rscale) * (args.col_scale ? __ldg(args.col_scale + col + i) : 1.f); }
           if (args.bias != nullptr && col + i < args.n_out) t += __ldg(args.bias + col + i);
-          if (args.relu) t = fmaxf(t, 0.f);
+          if (args.relu) t = t < 0.f ? 0.f : t;            // NaN passes, like torch.relu
           v[i] = t;
           hi[i] = to_tf32(t);
           lo[i] = to_tf32(t - hi[i]);

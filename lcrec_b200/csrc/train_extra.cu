@@ -96,7 +96,7 @@ bn_apply_kernel(const float* __restrict__ y, const double* __restrict__ sums, in
   for (int64_t r = r0 + rl; r < r1; r += nrl) {
     const int64_t o = r * C + c;
     float v = (y[o] - mu) * is * ga + be;
-    if (relu) v = v > 0.f ? v : 0.f;
+    if (relu) v = v < 0.f ? 0.f : v;                      // NaN passes, like torch.relu
     out[o] = v;
   }
 }
