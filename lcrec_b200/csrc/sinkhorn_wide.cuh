@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
   int* misc = reinterpret_cast<int*>(mm + 4);                         // [0] risky of this CTA
   const int ncols = (Kc + kWideThreads - 1) / kWideThreads;           // columns this thread owns: tid + 1024 c (c < ncols) if < Kc
   const int n_work = *a.count;
-  const double Kd = (double)K;
+  const double Kd = (double)K, invK = 1.0 / Kd;
+  const bool kpow2 = (K & (K - 1)) == 0;
   const unsigned n_clusters = gridDim.x / C, cluster_id = blockIdx.x / C;
   bool bad = false;
   unsigned parity = 0;                                                // exchange-buffer parity, advances with every exchange
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) sinkhorn_wide_kernel(const Sk
           for (int i = 0; i < n; ++i) cs = __dadd_rn(cs, __dmul_rn(__dmul_rn(u_s[i], E[(size_t)i * Kc + kl]), v[c]));
           for (int i = 0; i < n; ++i) {
             const double q = __dmul_rn(__dmul_rn(u_s[i], E[(size_t)i * Kc + kl]), v[c]);
-            const double val = __dmul_rn(__ddiv_rn(__ddiv_rn(q, cs), Kd), Bd);
+            const double val = __dmul_rn(kpow2 ? __dmul_rn(__ddiv_rn(q, cs), invK) : __ddiv_rn(__ddiv_rn(q, cs), Kd), Bd);   // / K is an exact multiply for K = 2^m
             bad = bad || isnan(val) || isinf(val);
             E[(size_t)i * Kc + kl] = val;
           }

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = C > 1 ? cluster.block_rank() : 0;
   const int n_work = *a.count;
-  const double Kd = (double)K;
+  const double Kd = (double)K, invK = 1.0 / Kd;
+  const bool kpow2 = (K & (K - 1)) == 0;
   const unsigned n_clusters = gridDim.x / C, cluster_id = blockIdx.x / C;
   bool bad = false;
   unsigned parity = 0;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) sinkhorn_widereg_kernel(const S
         for (int i = 0; i < RM; ++i)
           if (i < n) {
             const double q = __dmul_rn(__dmul_rn(u_s[cur][i], E[i][c]), vc);
-            const double val = __dmul_rn(__ddiv_rn(__ddiv_rn(q, cs), Kd), Bd);
+            const double val = __dmul_rn(kpow2 ? __dmul_rn(__ddiv_rn(q, cs), invK) : __ddiv_rn(__ddiv_rn(q, cs), Kd), Bd);   // / K is an exact multiply for K = 2^m
             bad = bad || isnan(val) || isinf(val);
             E[i][c] = val;
           }
