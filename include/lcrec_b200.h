@@ -423,6 +423,14 @@ int lcrec_exchange_unpack(const void* recv, int world, int64_t slab_rows, int n_
 int lcrec_exchange_pack_last(const int64_t* codes, int n_levels, const void* recv, int world, int64_t slab_rows, int e_dim,
                              int64_t* back, int64_t n_rows_hint, void* stream);
 int lcrec_exchange_scatter_last(const int64_t* back_recv, const int32_t* slot, int64_t n, int n_levels, int64_t* codes, void* stream);
+/* A/B switch: 1 (default) = collision groups of 9..32 rows at codebooks of <= 256 codes run on the column kernels (one thread
+ * per code, kernel matrix in registers), 0 = on the shared-memory CTA kernel as in round 1.  Results are identical. */
+int lcrec_sinkhorn_set_col(int on);
+/* Self-check of the shared-reciprocal IEEE division of the per-group Sinkhorn kernels (its last column step divides every row
+ * of a column by the same sum): counts[0] += pairs (a[i], b[i]) whose quotient differs from the device's IEEE a / b although
+ * the range check of the fast sequence passed (must stay 0), counts[1] += pairs the range check sends to the fallback.
+ * counts: 2 x u64 on the device, accumulated (zero them first). */
+int lcrec_ddiv_probe(const double* a, const double* b, int64_t n, uint64_t* counts, void* stream);
 /* Measured fp64 FMA peak of the device in FLOP/s (8 independent DFMA chains per thread, 148 x 8 CTAs): the denominator of the
  * fp64-pipe fraction bench.py reports for the per-group Sinkhorn (MEASURED_PEAKS.json carries no fp64 figure).  ws: >= 8 B x SMs x 2048.
  * Synchronises the stream. */

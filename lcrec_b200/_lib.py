@@ -108,6 +108,8 @@ SIGNATURES = {
     "lcrec_index_json_workspace_bytes": (i64, [i64]),
     "lcrec_index_json": (C.c_int, [vp, i64, C.c_int, vp, i64, vp, vp, i64, vp]),
     "lcrec_fp64_peak_probe": (C.c_int, [C.POINTER(f64), vp, i64, vp]),
+    "lcrec_ddiv_probe": (C.c_int, [vp, vp, i64, vp, vp]),
+    "lcrec_sinkhorn_set_col": (C.c_int, [C.c_int]),
     "lcrec_exchange_record_bytes": (i64, [C.c_int, C.c_int]),
     "lcrec_exchange_slab_bytes": (i64, [i64, C.c_int, C.c_int]),
     "lcrec_exchange_workspace_bytes": (i64, [i64, C.c_int]),

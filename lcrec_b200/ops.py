@@ -65,6 +65,23 @@ def fp64_peak_tflops(device=None) -> float:
     return out.value / 1e12
 
 
+def sinkhorn_set_col(on: bool) -> None:
+    """A/B switch of the column kernels for collision groups of 9..32 rows (lcrec_sinkhorn_set_col); results are identical."""
+    _lib.check(_lib.load().lcrec_sinkhorn_set_col(int(bool(on))))
+
+
+def ddiv_probe(a: torch.Tensor, b: torch.Tensor):
+    """(wrong, fallback) of lcrec_ddiv_probe over the fp64 device pairs (a[i], b[i]): quotients of the shared-reciprocal
+    division that differ from the device's IEEE a / b (must be 0) and pairs its range check hands to the fallback."""
+    assert a.is_cuda and a.dtype == torch.float64 and b.dtype == torch.float64 and a.numel() == b.numel()
+    a, b = a.contiguous(), b.contiguous()
+    counts = torch.zeros(2, dtype=torch.int64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().lcrec_ddiv_probe(_p(a), _p(b), a.numel(), _p(counts), C.c_void_p(torch.cuda.current_stream(a.device).cuda_stream)))
+    w, f = counts.tolist()
+    return int(w), int(f)
+
+
 def profile_enable(on: bool) -> None:
     _lib.check(_lib.load().lcrec_profile_enable(int(on)))
 

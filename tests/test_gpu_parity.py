@@ -279,7 +279,7 @@ def test_sinkhorn_group_modes_agree(k, d):
     2..12 plus a few large): the default filtered mode (2) must give exactly the codes of the all-literal
     mode (0); the pure scaling form (1) may differ on ulp-level ties only (counted, < 1e-4 of rows)."""
     rng = np.random.default_rng(11)
-    sizes = np.concatenate([rng.integers(2, 13, size=30000), [40, 99, 100, 150]])
+    sizes = np.concatenate([rng.integers(2, 13, size=30000), rng.integers(13, 34, size=400), [40, 99, 100, 150]])
     n_items = int(sizes.sum())
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     centres = (rng.standard_normal((len(sizes), d)) * 0.05).astype(np.float32)
@@ -302,9 +302,18 @@ def test_sinkhorn_group_modes_agree(k, d):
                                      len(sizes), n_items, 0.003, 50, codes, 3)
             assert fl == 0
             out[mode] = codes.cpu().numpy()[:, 3]
+        # groups of 9..32 rows: the column kernels (default) against the shared-memory CTA kernel, filtered mode
+        ops.sinkhorn_set_mode(2)
+        ops.sinkhorn_set_col(False)
+        codes = torch.zeros((n_items, 4), dtype=torch.int64, device=DEV)
+        ops.sinkhorn_groups(T(resid_items), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV),
+                            len(sizes), n_items, 0.003, 50, codes, 3)
+        out["cta"] = codes.cpu().numpy()[:, 3]
     finally:
         ops.sinkhorn_set_mode(2)
+        ops.sinkhorn_set_col(True)
     assert (out[2] != out[0]).sum() == 0, int((out[2] != out[0]).sum())
+    assert (out["cta"] != out[0]).sum() == 0, int((out["cta"] != out[0]).sum())
     assert (out[1] != out[0]).mean() < 1e-4
     # spot-check against the numpy oracle on the first 300 groups, distances evaluated in the kernels' summation order (fma
     # chains): every row must agree; a differing row is COUNTED only if the oracle's own plan holds the two columns within
@@ -743,3 +752,33 @@ def test_trainer_matches_reference_losses(golden, tmp_path):
     np.testing.assert_allclose(np.array(losses), g["losses"], rtol=2e-3)
     coll = tr._valid_epoch(loader)
     assert abs(coll - float(g["collision_rate"])) < 0.02
+
+
+@pytest.mark.gpu
+def test_shared_reciprocal_division_is_ieee():
+    """The last column step of the per-group Sinkhorn divides every row of a column by the same sum; the warp kernels form the
+    reciprocal once per column (the sequence of the device's own double division) - its quotients must be the IEEE ones on
+    everything the range check lets through: uniform operands, shares of a column sum (q <= cs, down to e^-660), near-ties."""
+    from lcrec_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(11)
+    n = 1 << 23
+    cases = []
+    a = torch.rand(n, dtype=torch.float64, device=DEV, generator=g) + 2.0 ** -60
+    b = torch.rand(n, dtype=torch.float64, device=DEV, generator=g) + 2.0 ** -60
+    cases.append((a, b))
+    # shares: cs = q + others, others spanning 600 e-folds either way
+    q = torch.exp((torch.rand(n, dtype=torch.float64, device=DEV, generator=g) - 0.5) * 600.0)
+    others = q * torch.exp((torch.rand(n, dtype=torch.float64, device=DEV, generator=g) - 0.5) * 1300.0)
+    cases.append((q, q + others))
+    # dominated columns: cs = q (1 + k 2^-52), k small
+    k = torch.randint(0, 64, (n,), device=DEV, generator=g).to(torch.float64)
+    cases.append((q, q * (1.0 + k * 2.0 ** -52)))
+    # wide dynamic range
+    e1 = torch.exp((torch.rand(n, dtype=torch.float64, device=DEV, generator=g) - 0.5) * 1200.0)
+    cases.append((a * e1, b))
+    total_fallback = 0
+    for x, y in cases:
+        wrong, fallback = ops.ddiv_probe(x, y)
+        assert wrong == 0, (wrong, fallback)
+        total_fallback += fallback
+    assert total_fallback < 0.2 * n * len(cases)      # the fast sequence covers the working range (fallbacks: subnormal / overflowing quotients)
