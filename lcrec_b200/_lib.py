@@ -79,6 +79,7 @@ SIGNATURES = {
     "lcrec_indexer_round": (C.c_int, [vp, i64, C.POINTER(i64), vp]),
     "lcrec_indexer_resolve": (C.c_int, [vp, vp, vp, i64, C.c_int, C.POINTER(i64), vp]),
     "lcrec_indexer_set_segments": (C.c_int, [C.c_int]),
+    "lcrec_indexer_set_speculative": (C.c_int, [C.c_int]),
     "lcrec_ema_update": (C.c_int, [vp, vp, i64, C.c_int, C.c_int, f64, f64, vp, vp, vp, vp]),
     "lcrec_codebook_usage": (C.c_int, [vp, C.c_int, f64, f64, vp, vp, vp]),
     "lcrec_masked_mean_pool_workspace_bytes": (i64, [i64, i64, C.c_int]),

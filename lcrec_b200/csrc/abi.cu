@@ -275,9 +275,22 @@ static int collide_and_fetch(lcrec_indexer_t* ix, const int64_t* codes, int64_t 
       LC_TRY(lcrec_collisions(codes, n, ix->L, ix->K.data(), ix->offsets, ix->members, ix->counts, ix->col_ws,
                               ix->col_ws_bytes, st));
   }
-  LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 6, cudaMemcpyDeviceToHost, st));
+  LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, st));
   LC_CUDA(cudaStreamSynchronize(st));
   return LCREC_OK;
+}
+
+// Later collision rounds without host round trips (lcrec_indexer_set_speculative; default OFF - measured on B200 at 1 M items:
+// the ~8 additional empty launches per round (every size class has to be enqueued blind) cost what the 19 host reads cost,
+// 4.13 vs 3.97 ms for rounds 2..20, profiles/r2_speculative_rounds.txt).  Once the first check inside the
+// prefix segments has passed (no segment too large for the on-chip sort - the segments never change afterwards, only last-level
+// codes do) every remaining round is enqueued back to back: check -> account -> Sinkhorn with worst-case launch bounds; the
+// kernels read the group count on the device and a round without collisions is a chain of empty launches.  The host reads the
+// counters once, after the final check.  Results are identical to the synchronous loop (tests/test_gpu_loop_ledger.py).
+static int g_speculative = 0;
+extern "C" int lcrec_indexer_set_speculative(int on) { g_speculative = on ? 1 : 0; return LCREC_OK; }
+__global__ void round_account_kernel(int64_t* counts) {      // counts[6] += rounds that resolved, counts[7] += their rows
+  if (counts[1] > 0) { counts[6] += 1; counts[7] += counts[2]; }
 }
 
 static int check_flags(int32_t f) {
@@ -320,6 +333,32 @@ static int rounds_impl(lcrec_indexer_t* ix, int64_t* codes, const float* resid, 
     }
     tot_rows += rows;
     ++rounds;
+    if (g_speculative && have_seg && seg_round >= 1 && ix->K[ix->L - 1] <= 256 && rounds < max_rounds) {
+      // the segments passed their first check (c[5] == 0 above): the rest of the loop runs without the host
+      for (int64_t r = rounds; r < max_rounds; ++r) {
+        {
+          ProfScope prof(21, st);
+          const int in = (seg_round + 1) & 1, out = seg_round & 1;
+          LC_CUDA(cudaMemsetAsync(ix->seg_active_count + out, 0, sizeof(int32_t), st));
+          LC_TRY(lcrec_collisions_in_segments_active(codes, n, ix->L, ix->L - 1, ix->seg_offsets, ix->seg_members, ix->seg_counts + 1,
+                                                     n / 2 + 1, ix->seg_active[in], ix->seg_active_count + in, ix->seg_active[out],
+                                                     ix->seg_active_count + out, ix->offsets, ix->members, ix->counts, ix->seg_ws,
+                                                     ix->seg_ws_bytes, st));
+          ++seg_round;
+          round_account_kernel<<<1, 1, 0, st>>>(ix->counts);
+          LC_LAUNCH_CHECK("round_account_kernel");
+        }
+        ProfScope prof(23, st);
+        LC_TRY(lcrec_sinkhorn_groups_ex(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members, ix->counts + 1,
+                                        n / 2, n, -1, ix->eps, ix->iters, codes, ix->L, ix->L - 1, 1, 0, ix->flags, ix->sk_ws,
+                                        ix->sk_ws_bytes, st));
+      }
+      LC_TRY(collide_and_fetch(ix, codes, n, seg_round++, st));      // the check after the last round (statistics, flags)
+      LC_TRY(check_flags((int32_t)(c[4] & 0xffffffff)));
+      rounds += c[6];
+      tot_rows += c[7];
+      break;
+    }
   }
   int32_t f[2];
   LC_CUDA(cudaMemcpyAsync(f, ix->flags, sizeof(f), cudaMemcpyDeviceToHost, st));

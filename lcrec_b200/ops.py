@@ -724,6 +724,11 @@ def indexer_set_segments(on: bool) -> None:
     _lib.check(_lib.load().lcrec_indexer_set_segments(int(bool(on))))
 
 
+def indexer_set_speculative(on: bool) -> None:
+    """Later collision rounds enqueued without host round trips, or one host read per round (default); identical results."""
+    _lib.check(_lib.load().lcrec_indexer_set_speculative(int(bool(on))))
+
+
 def sort_codes(codes: torch.Tensor, n_codes: Sequence[int]):
     _need_cuda(codes)
     lib = _lib.load()
