@@ -429,8 +429,9 @@ int lcrec_exchange_unpack(const void* recv, int world, int64_t slab_rows, int n_
 int lcrec_exchange_pack_last(const int64_t* codes, int n_levels, const void* recv, int world, int64_t slab_rows, int e_dim,
                              int64_t* back, int64_t n_rows_hint, void* stream);
 int lcrec_exchange_scatter_last(const int64_t* back_recv, const int32_t* slot, int64_t n, int n_levels, int64_t* codes, void* stream);
-/* A/B switch: 1 (default) = collision groups of 9..32 rows at codebooks of <= 256 codes run on the column kernels (one thread
- * per code, kernel matrix in registers), 0 = on the shared-memory CTA kernel as in round 1.  Results are identical. */
+/* A/B switch for codebooks of <= 256 codes: 0 = collision groups of 9..32 rows run on the shared-memory CTA kernel as in round 1,
+ * 1 = on the column kernels (one thread per code, kernel matrix in registers), 2 (default) = additionally every group of a call
+ * with few (<= 888) groups - the late collision rounds, bound by the latency of one group.  Results are identical. */
 int lcrec_sinkhorn_set_col(int on);
 /* Self-check of the shared-reciprocal IEEE division of the per-group Sinkhorn kernels (its last column step divides every row
  * of a column by the same sum): counts[0] += pairs (a[i], b[i]) whose quotient differs from the device's IEEE a / b although

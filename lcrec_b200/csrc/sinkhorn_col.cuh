@@ -1,4 +1,7 @@
-// Per-group Sinkhorn for collision groups of 9..32 rows at small codebooks (K <= 256 codes) - included by sinkhorn.cu.
+// Per-group Sinkhorn with one thread per code at small codebooks (K <= 256 codes) - included by sinkhorn.cu.  Serves the groups of
+// 9..32 rows (RM = 16 / 32) of every round and, with RM = 4 / 8, ALL groups of a late collision round that holds only a few
+// hundred of them: a late round is bound by the latency of one group, and a group spread over K threads runs ~50 dependent
+// instructions per iteration where the warp kernel (one warp per group, 8 columns per lane) runs 113.
 //
 // The CTA kernel (sinkhorn_groups_kernel) keeps the n x K kernel matrix in shared memory and every FMA of the 50 iterations
 // pays an 8-byte shared-memory read: 6.5 % of the fp64 pipe (ncu, profiles/r2_sk256_*).  Here the CTA has one THREAD PER
@@ -15,8 +18,9 @@ template <int RM> struct SkColShape { static constexpr int MINB = RM <= 16 ? 3 :
 template <int RM, bool FILTER>
 __global__ void __launch_bounds__(256, SkColShape<RM>::MINB) sinkhorn_groups_col_kernel(const SkGroupArgs a) {
   extern __shared__ __align__(16) unsigned char sk_smem[];
-  constexpr int LOGRM = RM == 16 ? 4 : 5;
-  static_assert(RM == 16 || RM == 32, "row classes of the column kernel");
+  constexpr int LOGRM = RM == 4 ? 2 : (RM == 8 ? 3 : (RM == 16 ? 4 : 5));
+  static_assert(RM == 4 || RM == 8 || RM == 16 || RM == 32, "row classes of the column kernel");
+  constexpr int kTail = 32 >> LOGRM;                     // lanes that still hold partials of the same row after the transposed stages
   const int T = blockDim.x, NW = T >> 5;                 // T == K
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = a.K, D = a.D;
@@ -128,8 +132,9 @@ __global__ void __launch_bounds__(256, SkColShape<RM>::MINB) sinkhorn_groups_col
           cur[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
       }
-      if constexpr (RM == 16) cur[0] += __shfl_xor_sync(0xffffffffu, cur[0], 1);
-      if (RM == 32 || (lane & 1) == 0) red[warp * RM + (lane >> (5 - LOGRM))] = cur[0];
+#pragma unroll
+      for (int o = kTail >> 1; o > 0; o >>= 1) cur[0] += __shfl_xor_sync(0xffffffffu, cur[0], o);
+      if ((lane & (kTail - 1)) == 0) red[warp * RM + (lane >> (5 - LOGRM))] = cur[0];
       __syncthreads();
       if (tid < RM) {
         double rs = 0.0;
@@ -196,12 +201,13 @@ __global__ void __launch_bounds__(256, SkColShape<RM>::MINB) sinkhorn_groups_col
         kk[j] = take ? ok : keep_k;
       }
     }
-    if constexpr (RM == 16) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv[0], 1);
-      const int ok = __shfl_xor_sync(0xffffffffu, kk[0], 1);
+#pragma unroll
+    for (int o = kTail >> 1; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv[0], o);
+      const int ok = __shfl_xor_sync(0xffffffffu, kk[0], o);
       if (arg_better(ov, ok, bv[0], kk[0])) { bv[0] = ov; kk[0] = ok; }
     }
-    if (RM == 32 || (lane & 1) == 0) {
+    if ((lane & (kTail - 1)) == 0) {
       red[warp * RM + (lane >> (5 - LOGRM))] = bv[0];
       red_k[warp * RM + (lane >> (5 - LOGRM))] = kk[0];
     }

@@ -65,9 +65,10 @@ def fp64_peak_tflops(device=None) -> float:
     return out.value / 1e12
 
 
-def sinkhorn_set_col(on: bool) -> None:
-    """A/B switch of the column kernels for collision groups of 9..32 rows (lcrec_sinkhorn_set_col); results are identical."""
-    _lib.check(_lib.load().lcrec_sinkhorn_set_col(int(bool(on))))
+def sinkhorn_set_col(on) -> None:
+    """A/B switch of the column kernels (lcrec_sinkhorn_set_col): False / 0 = off, 1 = groups of 9..32 rows only, True / 2 (default)
+    = also every group of a call with few groups (late collision rounds); results are identical."""
+    _lib.check(_lib.load().lcrec_sinkhorn_set_col(2 if on is True else int(on)))
 
 
 def ddiv_probe(a: torch.Tensor, b: torch.Tensor):

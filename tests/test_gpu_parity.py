@@ -309,9 +309,24 @@ def test_sinkhorn_group_modes_agree(k, d):
         ops.sinkhorn_groups(T(resid_items), T(cb), T(off), T(mem), torch.tensor([len(sizes)], device=DEV),
                             len(sizes), n_items, 0.003, 50, codes, 3)
         out["cta"] = codes.cpu().numpy()[:, 3]
+        # a late collision round: a call with few groups runs EVERY group on the column kernels (one thread per code, RM = 4 / 8 /
+        # 16 / 32) - against the warp kernels (col = 1) and the literal mode on the same 800 groups
+        sub = np.r_[0:700, len(sizes) - 100:len(sizes)]                      # sizes 2..12, 13..33 and the large ones
+        sub_off = np.concatenate([[0], np.cumsum(sizes[sub])]).astype(np.int64)
+        sub_mem = np.concatenate([mem[off[g]:off[g + 1]] for g in sub]).astype(np.int64)
+        for col in (2, 1):
+            ops.sinkhorn_set_col(col)
+            codes = torch.zeros((n_items, 4), dtype=torch.int64, device=DEV)
+            fl = ops.sinkhorn_groups(T(resid_items), T(cb), T(sub_off), T(sub_mem), torch.tensor([len(sub)], device=DEV),
+                                     len(sub), len(sub_mem), 0.003, 50, codes, 3)
+            assert fl == 0
+            out[f"late{col}"] = codes.cpu().numpy()[sub_mem, 3]
+        out["late_ref"] = out[0][sub_mem]
     finally:
         ops.sinkhorn_set_mode(2)
         ops.sinkhorn_set_col(True)
+    assert (out["late2"] != out["late_ref"]).sum() == 0 and (out["late1"] != out["late_ref"]).sum() == 0, \
+        (int((out["late2"] != out["late_ref"]).sum()), int((out["late1"] != out["late_ref"]).sum()))
     assert (out[2] != out[0]).sum() == 0, int((out[2] != out[0]).sum())
     assert (out["cta"] != out[0]).sum() == 0, int((out["cta"] != out[0]).sum())
     assert (out[1] != out[0]).mean() < 1e-4
