@@ -323,8 +323,8 @@ def run_gpu_arm(a):
             os.close(saved)
     pk = peaks()
     ops.set_default_engine(a.engine)
-    if os.environ.get("LCREC_SPECULATIVE") == "1":      # A/B: rounds 3..20 enqueued without host reads of the collision counts (default: one per round)
-        ops.indexer_set_speculative(True)
+    if os.environ.get("LCREC_SPECULATIVE") in ("0", "1", "2"):      # A/B of the late collision rounds: 0 host read per round, 1 blind, 2 graph replays (default)
+        ops.indexer_set_speculative(int(os.environ["LCREC_SPECULATIVE"]))
     ws, bs, cbs, head = make_model()
     n_local = a.items
     model = RQVAE(in_dim=DIMS[0], num_emb_list=N_CODES, e_dim=E_DIM, layers=DIMS[1:-1], sk_epsilons=[0.0, 0.0, 0.0, EPS_LAST],

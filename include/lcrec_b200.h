@@ -343,11 +343,12 @@ int lcrec_indexer_resolve(lcrec_indexer_t* ix, int64_t* codes, const float* resi
 /* 1 (default): from the second round on, collisions are searched inside the prefix segments (no global re-sort);
  * 0: every round re-sorts all items.  Results are identical; process-wide switch for cross-checks. */
 int lcrec_indexer_set_segments(int on);
-/* 1: once the first check inside the prefix segments has passed, the remaining rounds of generate_indices.py:108-128
- * are enqueued back to back (check -> Sinkhorn with worst-case launch bounds, group counts read on the device) and the host
- * reads the counters once at the end; 0 (default): one host read of the counts per round.  Results and stats are identical
- * (tests/test_gpu_loop_ledger.py); measured no faster on one B200 (the blind launches of every size class cost what the host
- * reads cost), kept as a switch.  Applies to last-level codebooks of <= 256 codes. */
+/* Later rounds of generate_indices.py:108-128 without a host read per round.  Once the first check inside the prefix segments has
+ * passed, a round can be enqueued blind (check -> Sinkhorn with worst-case launch bounds, group counts read on the device):
+ * 0 = one host read of the counts per round; 1 = every remaining round enqueued blind on the caller's stream (measured no faster:
+ * the host's launch rate becomes the bound); 2 (default) = as soon as a round has <= 888 groups the blind round is captured once
+ * into a CUDA graph and the remaining rounds are graph replays in batches of 6 with one host read per batch.  Results and stats
+ * are identical (tests/test_gpu_loop_ledger.py).  Applies to last-level codebooks of <= 256 codes; process-wide switch. */
 int lcrec_indexer_set_speculative(int on);
 int64_t* lcrec_indexer_codes(lcrec_indexer_t* ix);      /* (max_items, L) int64 device */
 float* lcrec_indexer_resid(lcrec_indexer_t* ix);        /* (max_items, e_dim) fp32 device */

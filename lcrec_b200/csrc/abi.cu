@@ -62,6 +62,7 @@ int num_sms() {
 
 // ---- per-stage profiling
 static bool g_prof_on = false;
+static bool g_prof_suspended = false;      // stream capture in progress: timing events must not become graph nodes
 struct ProfPair { cudaEvent_t a, b; int tag; };
 static std::vector<ProfPair> g_prof_pairs;
 static std::vector<cudaEvent_t> g_prof_pool;
@@ -73,14 +74,14 @@ static cudaEvent_t prof_event() {
 }
 void prof_begin(int tag, cudaStream_t st) {
   nvtxRangePushA(stage_name(tag));
-  if (!g_prof_on || tag < 0 || tag >= kProfTags) return;
+  if (!g_prof_on || g_prof_suspended || tag < 0 || tag >= kProfTags) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, st);
   g_prof_open[tag] = e;
 }
 void prof_end(int tag, cudaStream_t st) {
   nvtxRangePop();
-  if (!g_prof_on || tag < 0 || tag >= kProfTags || !g_prof_open[tag]) return;
+  if (!g_prof_on || g_prof_suspended || tag < 0 || tag >= kProfTags || !g_prof_open[tag]) return;
   cudaEvent_t e = prof_event();
   cudaEventRecord(e, st);
   g_prof_pairs.push_back({g_prof_open[tag], e, tag});
@@ -162,6 +163,12 @@ struct lcrec_indexer {
   int64_t* counts_host = nullptr;   // pinned: 4 counts + flags
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  // late collision rounds as CUDA-graph replays (one graph per parity of the active-segment ping-pong)
+  cudaStream_t round_stream = nullptr; cudaEvent_t round_ev = nullptr;
+  cudaGraphExec_t round_exec[2] = {nullptr, nullptr};
+  int64_t round_launches[2] = {0, 0};
+  const int64_t* rg_codes = nullptr; const float* rg_resid = nullptr; int64_t rg_n = -1; int rg_key = -1;
+  bool rg_failed = false;
 };
 
 extern "C" int lcrec_mlp_in_dim(const lcrec_mlp_t* m);
@@ -226,6 +233,9 @@ extern "C" int lcrec_indexer_destroy(lcrec_indexer_t* ix) {
   if (ix->counts_host) cudaFreeHost(ix->counts_host);
   for (int i = 0; i < 2; ++i) { if (ix->ev_copied[i]) cudaEventDestroy(ix->ev_copied[i]); if (ix->ev_consumed[i]) cudaEventDestroy(ix->ev_consumed[i]); }
   if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
+  for (int i = 0; i < 2; ++i) if (ix->round_exec[i]) cudaGraphExecDestroy(ix->round_exec[i]);
+  if (ix->round_ev) cudaEventDestroy(ix->round_ev);
+  if (ix->round_stream) cudaStreamDestroy(ix->round_stream);
   delete ix;
   return LCREC_OK;
 }
@@ -280,17 +290,80 @@ static int collide_and_fetch(lcrec_indexer_t* ix, const int64_t* codes, int64_t 
   return LCREC_OK;
 }
 
-// Later collision rounds without host round trips (lcrec_indexer_set_speculative; default OFF - measured on B200 at 1 M items:
-// the ~8 additional empty launches per round (every size class has to be enqueued blind) cost what the 19 host reads cost,
-// 4.13 vs 3.97 ms for rounds 2..20, profiles/r2_speculative_rounds.txt).  Once the first check inside the
+// Later collision rounds without a host round trip per round (lcrec_indexer_set_speculative).  Once the first check inside the
 // prefix segments has passed (no segment too large for the on-chip sort - the segments never change afterwards, only last-level
-// codes do) every remaining round is enqueued back to back: check -> account -> Sinkhorn with worst-case launch bounds; the
-// kernels read the group count on the device and a round without collisions is a chain of empty launches.  The host reads the
-// counters once, after the final check.  Results are identical to the synchronous loop (tests/test_gpu_loop_ledger.py).
-static int g_speculative = 0;
-extern "C" int lcrec_indexer_set_speculative(int on) { g_speculative = on ? 1 : 0; return LCREC_OK; }
+// codes do) a round can be enqueued BLIND: check -> account -> Sinkhorn with worst-case launch bounds; the kernels read the group
+// count on the device and a round without collisions is a chain of empty launches.
+//   0: one host read of the counts per round (the synchronous loop);
+//   1: every remaining round enqueued blind on the caller's stream, one host read at the end.  Measured NOT faster on one B200
+//      (profiles/r2_speculative_rounds.txt): ~20 launches per round, the host's launch rate becomes the bound;
+//   2 (default): as soon as a round has at most kLateGroups groups the blind round is captured ONCE into a CUDA graph (two graphs:
+//      the active-segment lists ping-pong) and the remaining rounds are graph replays in batches of kRoundBatch with one host
+//      read per batch (stop when a check finds no group).  Late rounds are bound by launch gaps and the latency of one group, not
+//      by work: a replay runs the ~16 nodes back to back.
+// Results and stats are identical in all three modes (tests/test_gpu_loop_ledger.py).
+static int g_speculative = 2;
+extern "C" int lcrec_indexer_set_speculative(int on) { g_speculative = on < 0 ? 0 : (on > 2 ? 2 : on); return LCREC_OK; }
+constexpr int64_t kLateGroups = 888;      // = kColLateGroups of sinkhorn.cu: from here on every group runs on the column kernels
+constexpr int kRoundBatch = 6;
 __global__ void round_account_kernel(int64_t* counts) {      // counts[6] += rounds that resolved, counts[7] += their rows
   if (counts[1] > 0) { counts[6] += 1; counts[7] += counts[2]; }
+}
+
+// One blind round on `st`: check number seg_round (>= 1) inside the segments, account, Sinkhorn.  hint: -1 = any group count,
+// -2 = few groups expected (column kernels for every size class)
+static int enqueue_blind_round(lcrec_indexer_t* ix, int64_t* codes, const float* resid, int64_t n, int seg_round, int64_t hint,
+                               cudaStream_t st) {
+  const int in = (seg_round + 1) & 1, out = seg_round & 1;
+  LC_CUDA(cudaMemsetAsync(ix->seg_active_count + out, 0, sizeof(int32_t), st));
+  LC_TRY(lcrec_collisions_in_segments_active(codes, n, ix->L, ix->L - 1, ix->seg_offsets, ix->seg_members, ix->seg_counts + 1,
+                                             n / 2 + 1, ix->seg_active[in], ix->seg_active_count + in, ix->seg_active[out],
+                                             ix->seg_active_count + out, ix->offsets, ix->members, ix->counts, ix->seg_ws,
+                                             ix->seg_ws_bytes, st));
+  round_account_kernel<<<1, 1, 0, st>>>(ix->counts);
+  LC_LAUNCH_CHECK("round_account_kernel");
+  return lcrec_sinkhorn_groups_ex(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members, ix->counts + 1,
+                                  n / 2, n, hint, ix->eps, ix->iters, codes, ix->L, ix->L - 1, 1, 0, ix->flags, ix->sk_ws,
+                                  ix->sk_ws_bytes, st);
+}
+
+namespace lcrec { int sinkhorn_config_key(); }      // sinkhorn.cu: the kernel-selection switches a captured round depends on
+
+// The two round graphs for (codes, resid, n) and the current kernel-selection switches; captured on the indexer's own stream
+// (the caller's may be the legacy default stream, which cannot be captured).  Nothing executes during capture.
+static int ensure_round_graphs(lcrec_indexer_t* ix, int64_t* codes, const float* resid, int64_t n) {
+  if (ix->rg_failed) return LCREC_ERR_CUDA;
+  if (!ix->round_stream) {
+    if (cudaStreamCreateWithFlags(&ix->round_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ix->round_ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ix->rg_failed = true; return LCREC_ERR_CUDA; }
+  }
+  const int key = sinkhorn_config_key();
+  if (ix->round_exec[0] && ix->round_exec[1] && ix->rg_codes == codes && ix->rg_resid == resid && ix->rg_n == n && ix->rg_key == key) return LCREC_OK;
+  for (int i = 0; i < 2; ++i) if (ix->round_exec[i]) { cudaGraphExecDestroy(ix->round_exec[i]); ix->round_exec[i] = nullptr; }
+  for (int parity = 0; parity < 2; ++parity) {
+    const int64_t l0 = g_launches.load();
+    g_prof_suspended = true;
+    cudaGraph_t graph = nullptr;
+    int rc = LCREC_OK;
+    if (cudaStreamBeginCapture(ix->round_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) rc = LCREC_ERR_CUDA;
+    if (rc == LCREC_OK) {
+      rc = enqueue_blind_round(ix, codes, resid, n, 2 + parity, -2, ix->round_stream);
+      if (cudaStreamEndCapture(ix->round_stream, &graph) != cudaSuccess || graph == nullptr) rc = rc == LCREC_OK ? LCREC_ERR_CUDA : rc;
+    }
+    g_prof_suspended = false;
+    ix->round_launches[parity] = g_launches.load() - l0;
+    g_launches.fetch_sub(ix->round_launches[parity]);      // capture launched nothing
+    if (rc == LCREC_OK && cudaGraphInstantiate(&ix->round_exec[parity], graph, 0) != cudaSuccess) rc = LCREC_ERR_CUDA;
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != LCREC_OK) {
+      (void)cudaGetLastError();
+      for (int i = 0; i < 2; ++i) if (ix->round_exec[i]) { cudaGraphExecDestroy(ix->round_exec[i]); ix->round_exec[i] = nullptr; }
+      ix->rg_failed = true;      // this indexer stays on the synchronous loop
+      return rc;
+    }
+  }
+  ix->rg_codes = codes; ix->rg_resid = resid; ix->rg_n = n; ix->rg_key = key;
+  return LCREC_OK;
 }
 
 static int check_flags(int32_t f) {
@@ -333,25 +406,38 @@ static int rounds_impl(lcrec_indexer_t* ix, int64_t* codes, const float* resid, 
     }
     tot_rows += rows;
     ++rounds;
-    if (g_speculative && have_seg && seg_round >= 1 && ix->K[ix->L - 1] <= 256 && rounds < max_rounds) {
-      // the segments passed their first check (c[5] == 0 above): the rest of the loop runs without the host
-      for (int64_t r = rounds; r < max_rounds; ++r) {
+    const bool blind_ok = have_seg && seg_round >= 1 && ix->K[ix->L - 1] <= 256 && rounds < max_rounds;
+    if (g_speculative == 2 && blind_ok && groups <= kLateGroups && ensure_round_graphs(ix, codes, resid, n) == LCREC_OK) {
+      // the rest of the loop as graph replays: the indexer's stream takes over from the caller's and hands back by a host wait
+      LC_CUDA(cudaEventRecord(ix->round_ev, st));
+      LC_CUDA(cudaStreamWaitEvent(ix->round_stream, ix->round_ev, 0));
+      int64_t enq = rounds;
+      while (enq < max_rounds) {
+        const int64_t b = std::min<int64_t>(kRoundBatch, max_rounds - enq);
         {
-          ProfScope prof(21, st);
-          const int in = (seg_round + 1) & 1, out = seg_round & 1;
-          LC_CUDA(cudaMemsetAsync(ix->seg_active_count + out, 0, sizeof(int32_t), st));
-          LC_TRY(lcrec_collisions_in_segments_active(codes, n, ix->L, ix->L - 1, ix->seg_offsets, ix->seg_members, ix->seg_counts + 1,
-                                                     n / 2 + 1, ix->seg_active[in], ix->seg_active_count + in, ix->seg_active[out],
-                                                     ix->seg_active_count + out, ix->offsets, ix->members, ix->counts, ix->seg_ws,
-                                                     ix->seg_ws_bytes, st));
-          ++seg_round;
-          round_account_kernel<<<1, 1, 0, st>>>(ix->counts);
-          LC_LAUNCH_CHECK("round_account_kernel");
+          ProfScope prof(23, ix->round_stream);      // (covers the checks of these rounds as well)
+          for (int64_t i = 0; i < b; ++i) {
+            const int parity = seg_round & 1;
+            LC_CUDA(cudaGraphLaunch(ix->round_exec[parity], ix->round_stream));
+            count_launch((int)ix->round_launches[parity]);
+            ++seg_round;
+          }
         }
+        enq += b;
+        LC_CUDA(cudaMemcpyAsync(ix->counts_host, ix->counts, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost, ix->round_stream));
+        LC_CUDA(cudaStreamSynchronize(ix->round_stream));
+        if (c[1] == 0) break;      // the last check found no group (and its Sinkhorn was a chain of empty launches)
+      }
+      if (c[1] != 0) LC_TRY(collide_and_fetch(ix, codes, n, seg_round++, st));      // max_rounds reached: the check after the last round
+      LC_TRY(check_flags((int32_t)(c[4] & 0xffffffff)));
+      rounds += c[6];
+      tot_rows += c[7];
+      break;
+    }
+    if (g_speculative == 1 && blind_ok) {
+      for (int64_t r = rounds; r < max_rounds; ++r) {
         ProfScope prof(23, st);
-        LC_TRY(lcrec_sinkhorn_groups_ex(resid, ix->D, ix->cb[ix->L - 1], ix->K[ix->L - 1], ix->offsets, ix->members, ix->counts + 1,
-                                        n / 2, n, -1, ix->eps, ix->iters, codes, ix->L, ix->L - 1, 1, 0, ix->flags, ix->sk_ws,
-                                        ix->sk_ws_bytes, st));
+        LC_TRY(enqueue_blind_round(ix, codes, resid, n, seg_round++, -1, st));
       }
       LC_TRY(collide_and_fetch(ix, codes, n, seg_round++, st));      // the check after the last round (statistics, flags)
       LC_TRY(check_flags((int32_t)(c[4] & 0xffffffff)));

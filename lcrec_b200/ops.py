@@ -725,9 +725,10 @@ def indexer_set_segments(on: bool) -> None:
     _lib.check(_lib.load().lcrec_indexer_set_segments(int(bool(on))))
 
 
-def indexer_set_speculative(on: bool) -> None:
-    """Later collision rounds enqueued without host round trips, or one host read per round (default); identical results."""
-    _lib.check(_lib.load().lcrec_indexer_set_speculative(int(bool(on))))
+def indexer_set_speculative(mode) -> None:
+    """Later collision rounds: 0 / False = one host read per round, 1 = all remaining rounds enqueued blind on the caller's stream,
+    2 / True (default) = late rounds (<= 888 groups) replayed from a CUDA graph in batches; identical results."""
+    _lib.check(_lib.load().lcrec_indexer_set_speculative(2 if mode is True else int(mode)))
 
 
 def sort_codes(codes: torch.Tensor, n_codes: Sequence[int]):
